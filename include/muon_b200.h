@@ -1,0 +1,120 @@
+/*
+ * muon_b200.h -- C ABI of the B200-native sparse hot path of scverse/muon.
+ *
+ * muon itself is pure Python and has no FFI: the reference boundary for this path is the
+ * Python signature of mu.atac.pp.tfidf / mu.atac.tl.lsi / mu.tl.mofa.
+ * This header is the boundary *below* that Python shim: every entry point is what a
+ * ctypes / cffi / pybind binding of the reference would bind for the arithmetic the
+ * reference delegates to scipy / ARPACK / mofapy2.  Each declaration cites the reference
+ * lines whose arithmetic it replaces (paths relative to the muon checkout).
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - return 0 on success, <0 on error; mub_last_error() returns a thread-local message.
+ *   - every pointer is a DEVICE pointer unless its name ends in _h (host).
+ *   - the library never allocates or frees caller memory; scratch space is passed in and
+ *     sized by the matching *_workspace_bytes() query.
+ *   - work is enqueued on the caller's stream (cudaStream_t passed as void*); nothing
+ *     synchronises unless documented.  Re-entrant, no global mutable state.
+ *   - CSR layout: indptr int64[n_rows+1], indices int32[nnz], values float32[nnz]
+ *     (nnz may exceed 2^31: 6e9 at BASELINE configs[1]).
+ *   - dense operands are row-major with a leading dimension `ld` (floats) that must be one
+ *     of the padded widths 32, 64 or 128; columns >= the logical width must be zero.
+ */
+#ifndef MUON_B200_H
+#define MUON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mub_stream_t; /* cudaStream_t */
+
+/* flags of mub_tfidf_* : keyword arguments of tfidf(), muon/_atac/preproc.py:18-21,101 */
+#define MUB_TFIDF_LOG_TF 1u    /* log_tf=True      preproc.py:103-104 */
+#define MUB_TFIDF_LOG_IDF 2u   /* log_idf=True     preproc.py:107-108 */
+#define MUB_TFIDF_LOG_TFIDF 4u /* log_tfidf=True   preproc.py:116-117 */
+#define MUB_TFIDF_NO_SCALE 8u  /* scale_factor in {None,0,1}: multiply skipped, preproc.py:101 */
+
+int mub_version(void);
+const char* mub_last_error(void);
+/* sm count, compute capability and L2 size of the current device */
+int mub_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ---- TF-IDF (muon/_atac/preproc.py:92-119) -------------------------------------------- */
+/* pass 1: row_sum[i] = sum_j c_ij (preproc.py:93);  col_sum[j] += sum_i c_ij (preproc.py:106).
+ * row_sum is overwritten, col_sum is ACCUMULATED (zero it first; allreduce it across
+ * cell shards before pass 2). */
+int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const float* data,
+                         int64_t n_rows, int32_t n_cols, float* row_sum, float* col_sum,
+                         mub_stream_t stream);
+int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const double* data,
+                         int64_t n_rows, int32_t n_cols, double* row_sum, double* col_sum,
+                         mub_stream_t stream);
+/* idf[j] = n_obs_total / col_sum[j], log1p if MUB_TFIDF_LOG_IDF (preproc.py:106-108) */
+int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags,
+                      float* idf, mub_stream_t stream);
+int mub_tfidf_idf_f64(const double* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags,
+                      double* idf, mub_stream_t stream);
+/* pass 2: out_ij = log1p(((1/r_i) * c_ij) * sf) * idf_j   (preproc.py:94-96,101-104,110-112,
+ * 116-117), association order as written.  data_out may alias data_in (in place). */
+int mub_tfidf_apply_f32(const int64_t* indptr, const int32_t* indices, const float* data_in,
+                        float* data_out, int64_t n_rows, int32_t n_cols, const float* row_sum,
+                        const float* idf, float scale_factor, uint32_t flags, mub_stream_t stream);
+int mub_tfidf_apply_f64(const int64_t* indptr, const int32_t* indices, const double* data_in,
+                        double* data_out, int64_t n_rows, int32_t n_cols, const double* row_sum,
+                        const double* idf, double scale_factor, uint32_t flags, mub_stream_t stream);
+
+/* ---- CSR x dense SpMM: the operator applications inside svds ------------------------------
+ * C[n_rows x ld] (=|+=) A * B[n_cols x ld].  Replaces scipy's csr_matvec / csc_matvec loop
+ * driven by ARPACK (scipy _svds.py:428-460 called from muon/_atac/tools.py:53) and the dense
+ * Y^T Z / Y W contractions of mofapy2 (called from muon/_core/tools.py:583-585).
+ * ld in {32,64,128}.  accumulate: 0 -> C = A*B, 1 -> C += A*B.
+ * row_counter: optional device int64 scratch word, zeroed by the caller, enabling dynamic row
+ * scheduling (recommended for skewed row lengths, e.g. transposed ATAC matrices); may be NULL. */
+int mub_spmm_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data,
+                     int64_t n_rows, int64_t n_cols, const float* B, int32_t ld, float* C,
+                     int32_t accumulate, unsigned long long* row_counter, mub_stream_t stream);
+
+/* ---- CSR transpose (one-time per matrix): builds the CSR of A^T so that A^T * Y is again a
+ * row-gather SpMM (scipy does the same implicitly through csc_matvec, _svds.py:447).
+ * Step 1 counts entries per column into t_count[n_cols+1] (int64, zeroed by caller, slot 0 unused
+ * so that an inclusive scan of t_count is t_indptr); the caller scans (any device scan), then
+ * step 2 scatters.  cursor: int64[n_cols] scratch, overwritten.  Entry order inside a
+ * transposed row is not deterministic (atomic slot claim) unless `sorted` != 0, in which case a
+ * per-row insertion pass restores ascending order. */
+int mub_csr_transpose_count(const int32_t* indices, int64_t nnz, int32_t n_cols, int64_t* t_count,
+                            mub_stream_t stream);
+int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const float* data,
+                           int64_t n_rows, int32_t n_cols, int64_t row_offset,
+                           const int64_t* t_indptr, int64_t* cursor, int32_t* t_indices,
+                           float* t_data, mub_stream_t stream);
+
+/* ---- tall-skinny Gram (the k x k contraction that is allreduced across cell shards) ------
+ * G[l x l] = Y^T Y for Y[n x ld] row-major, float64 result (partials are fp32 per CTA slab,
+ * combined in fp64 in a fixed order: deterministic).  Replaces the dense Gram inside
+ * scipy.linalg.svd(Av) (_svds.py:511-521) and mofapy2's Z^T Z / W^T diag(tau) W.
+ * weights: optional per-row weight w_i (G = Y^T diag(w) Y), may be NULL. */
+size_t mub_gram_workspace_bytes(int64_t n, int32_t ld);
+int mub_gram_f32(const float* Y, const float* weights, int64_t n, int32_t ld, int32_t l, double* G,
+                 void* workspace, mub_stream_t stream);
+
+/* ---- synthetic ATAC count generator (benchmark / test input) ---------------
+ * Deterministic counter-based planted-topic model; bit-identical to the numpy generator in
+ * muon_b200/_synth.py.  Step 1 writes nnz per row; caller scans into indptr; step 2 fills.
+ * beta[n_cols], topic[n_topics x n_cols], row_topic[n_rows], row_scale[n_rows] are host-made
+ * tables (device copies); row0 is the global index of the first row (shards hash identically). */
+int mub_synth_count(int64_t row0, int64_t n_rows, int32_t n_cols, const float* beta, const float* topic,
+                    const int32_t* row_topic, const float* row_scale, uint64_t seed, int64_t* row_nnz,
+                    mub_stream_t stream);
+int mub_synth_fill(int64_t row0, int64_t n_rows, int32_t n_cols, const float* beta, const float* topic,
+                   const int32_t* row_topic, const float* row_scale, uint64_t seed, const int64_t* indptr,
+                   int32_t* indices, float* data, mub_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUON_B200_H */

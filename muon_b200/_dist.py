@@ -1,0 +1,34 @@
+"""torch.distributed plumbing for cell-sharded runs (one process per GPU).
+
+Every collective on the hot path is a sum-allreduce of a small replicated object (column
+sums [D], A_r^T Y_r [D x l], Gram [l x l], z-score moments [2k]).  With no process group
+(single GPU) these are no-ops.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def is_distributed() -> bool:
+    return torch.distributed.is_available() and torch.distributed.is_initialized() \
+        and torch.distributed.get_world_size() > 1
+
+
+def world_size() -> int:
+    return torch.distributed.get_world_size() if is_distributed() else 1
+
+
+def rank() -> int:
+    return torch.distributed.get_rank() if is_distributed() else 0
+
+
+def all_reduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    if is_distributed():
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+    return t
+
+
+def all_reduce_max_(t: torch.Tensor) -> torch.Tensor:
+    if is_distributed():
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return t

@@ -1,0 +1,94 @@
+"""ctypes binding of ``libmuon_b200.so`` (the C ABI declared in include/muon_b200.h).
+
+The library is built in-tree by ``python __graft_entry__.py build`` (``make -C
+muon_b200/csrc``).  There is deliberately NO fallback: if the shared object is missing or a
+call fails, the product path raises.  torch is used by callers for device memory and
+streams only; pointers cross this boundary as plain integers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmuon_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+i64, i32, u32, u64, f32, f64, vp = C.c_int64, C.c_int32, C.c_uint32, C.c_uint64, C.c_float, C.c_double, C.c_void_p
+
+# name -> argtypes (restype is int unless noted).  Keep in sync with include/muon_b200.h;
+# tests/test_cabi.py parses the header and checks every declared symbol is listed and exported.
+SIGNATURES = {
+    "mub_version": [],
+    "mub_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)],
+    "mub_tfidf_reduce_f32": [vp, vp, vp, i64, i32, vp, vp, vp],
+    "mub_tfidf_reduce_f64": [vp, vp, vp, i64, i32, vp, vp, vp],
+    "mub_tfidf_idf_f32": [vp, i32, f64, u32, vp, vp],
+    "mub_tfidf_idf_f64": [vp, i32, f64, u32, vp, vp],
+    "mub_tfidf_apply_f32": [vp, vp, vp, vp, i64, i32, vp, vp, f32, u32, vp],
+    "mub_tfidf_apply_f64": [vp, vp, vp, vp, i64, i32, vp, vp, f64, u32, vp],
+    "mub_spmm_csr_f32": [vp, vp, vp, i64, i64, vp, i32, vp, i32, vp, vp],
+    "mub_csr_transpose_count": [vp, i64, i32, vp, vp],
+    "mub_csr_transpose_fill": [vp, vp, vp, i64, i32, i64, vp, vp, vp, vp, vp],
+    "mub_gram_f32": [vp, vp, i64, i32, i32, vp, vp, vp],
+    "mub_synth_count": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp],
+    "mub_synth_fill": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp, vp, vp],
+}
+SPECIAL_RESTYPE = {
+    "mub_last_error": ([], C.c_char_p),
+    "mub_gram_workspace_bytes": ([i64, i32], C.c_size_t),
+}
+
+TFIDF_LOG_TF, TFIDF_LOG_IDF, TFIDF_LOG_TFIDF, TFIDF_NO_SCALE = 1, 2, 4, 8
+
+
+class MuonB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes library; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise MuonB200Error(
+                f"{LIB_PATH} is missing: build the CUDA extension first "
+                "(python __graft_entry__.py build, or make -C muon_b200/csrc). "
+                "muon_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        for name, (argtypes, restype) in SPECIAL_RESTYPE.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise MuonB200Error with mub_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.mub_last_error()
+        raise MuonB200Error(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None as an integer for ctypes."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,91 @@
+"""``mu.atac.pp`` -- ATAC preprocessing.  Only ``tfidf`` is on the hot path."""
+from __future__ import annotations
+
+from typing import Optional, Union
+from warnings import warn
+
+import numpy as np
+
+from .._containers import is_anndata, is_mudata, view_to_actual
+
+
+def _canonical_csr(counts):
+    """Host-side canonicalisation matching what scipy's matmul does to the reference's output
+    pattern: duplicates summed, explicit zeros dropped, indices sorted."""
+    import scipy.sparse as sp
+    X = counts if sp.isspmatrix_csr(counts) else sp.csr_matrix(counts)
+    if not X.has_canonical_format or (X.nnz and np.any(X.data == 0)):
+        X = X.copy()
+        X.sum_duplicates()
+        X.eliminate_zeros()
+        X.sort_indices()
+    return X
+
+
+def tfidf(
+    data,
+    log_tf: bool = True,
+    log_idf: bool = True,
+    log_tfidf: bool = False,
+    scale_factor: Union[int, float] = 1e4,
+    inplace: bool = True,
+    copy: bool = False,
+    from_layer: Optional[str] = None,
+    to_layer: Optional[str] = None,
+):
+    """Transform peak counts with TF-IDF -- drop-in for ``muon.atac.pp.tfidf``
+    (reference muon/_atac/preproc.py:16-129; same arguments, errors, and slot rebinding).
+
+    TF: counts normalised by the total per cell; IDF: number of cells over the total per peak;
+    by default ``log1p(TF * scale_factor) * log1p(IDF)`` is stored.
+
+    The arithmetic runs on the GPU (fused two-pass CSR kernel, ``csrc/tfidf.cu``) in the
+    floating dtype of the counts (float32 stays float32, float64 stays float64, integer counts
+    are computed in float64 like the reference).  ``adata.X`` may be a scipy sparse matrix, a
+    dense ndarray (result is a ``csr_matrix`` exactly like the reference, preproc.py:113-114)
+    or a device-resident :class:`muon_b200.DeviceCSR`, in which case the result stays in HBM.
+    """
+    from .. import _device
+
+    if is_anndata(data):
+        adata = data
+    elif is_mudata(data) and "atac" in data.mod:
+        adata = data.mod["atac"]
+    else:
+        raise TypeError("Expected AnnData or MuData object with 'atac' modality")
+
+    if log_tfidf and (log_tf or log_idf):
+        raise AttributeError(
+            "When returning log(TF*IDF), applying neither log(TF) nor log(IDF) is possible.")
+    if copy and not inplace:
+        raise ValueError("`copy=True` cannot be used with `inplace=False`.")
+    if to_layer is not None and not inplace:
+        raise ValueError(f"`to_layer='{str(to_layer)}'` cannot be used with `inplace=False`.")
+
+    if copy:
+        adata = adata.copy()
+    view_to_actual(adata)
+
+    counts = adata.X if from_layer is None else adata.layers[from_layer]
+    if to_layer is not None and to_layer in adata.layers:
+        warn(f"Existing layer '{str(to_layer)}' will be overwritten")
+
+    if isinstance(counts, _device.DeviceCSR):
+        res = _device.tfidf_csr(counts, log_tf, log_idf, log_tfidf, scale_factor)
+    else:
+        X = _canonical_csr(counts)
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)  # integer counts -> float64, SURVEY App. A.2
+        dev = _device.DeviceCSR.from_scipy(X)
+        out = _device.tfidf_csr(dev, log_tf, log_idf, log_tfidf, scale_factor, inplace_values=True)
+        # the sparsity pattern is untouched on the device: reuse the host index arrays
+        res = out.get(indptr_host=X.indptr, indices_host=X.indices)
+
+    if not inplace:
+        return res
+    if to_layer is not None:
+        adata.layers[to_layer] = res
+    else:
+        adata.X = res
+    if copy:
+        return adata

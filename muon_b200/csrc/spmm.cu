@@ -1,0 +1,153 @@
+// K2/K3 -- CSR x dense SpMM  C[n x P] (+)= A[n x d] * B[d x P]  for sm_100a, P in {32,64,128}.
+//
+// Replaces the per-Lanczos-step csr_matvec/csc_matvec pair that ARPACK drives inside
+// scipy.sparse.linalg.svds (scipy _svds.py:428-460, called at muon/_atac/tools.py:53) by a
+// blocked operator application on P vectors at once, and mofapy2's dense Y^T Z / Y W
+// contractions (muon/_core/tools.py:583-585).  A^T * Y uses the same kernel on the CSR of
+// A^T (transpose.cu).
+//
+// v1 "row-warp" kernel: a warp owns a row.  Lane layout: P/4 lanes cover one dense row as
+// float4 (16 B per lane, 4P bytes per non-zero, fully coalesced), so a warp consumes
+// G = 128/P non-zeros per gather instruction.  Column indices and values are streamed in
+// coalesced 128 B segments (32 per warp load, L1::no_allocate) and broadcast by shuffle;
+// 32/G independent float4 gathers are in flight per lane.  fp32 FMA accumulation in
+// registers, one float4 store per lane group at the end of the row.
+//
+// Traffic model: HBM streams 8 B/nnz (+ dense operands once); every non-zero
+// additionally pulls 4P bytes of B through L2->L1, which is the practical limiter at P>=32.
+#include "common.cuh"
+
+namespace mub {
+
+constexpr int kSpmmThreads = 256;
+constexpr int kSpmmWarps = kSpmmThreads / kWarp;
+
+template <int P>
+__device__ __forceinline__ void spmm_row(const int32_t* __restrict__ indices, const float* __restrict__ data,
+                                         int64_t start, int64_t end, const float* __restrict__ B,
+                                         float* __restrict__ C_row, int accumulate, int lane) {
+    constexpr int LPN = P / 4;    // lanes per non-zero
+    constexpr int G = 32 / LPN;   // non-zeros per warp-wide gather
+    constexpr int STEPS = 32 / G; // gathers per 32-nnz segment
+    const int sub = lane % LPN, grp = lane / LPN;
+    const float* Bl = B + sub * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t base = start;
+    // full 32-nnz segments: all STEPS gathers issued back to back
+    for (; base + 32 <= end; base += 32) {
+        const int c = ld_stream(indices + base + lane);
+        const float v = ld_stream(data + base + lane);
+        constexpr int BATCH = STEPS < 16 ? STEPS : 16;  // gathers in flight per lane
+#pragma unroll
+        for (int t0 = 0; t0 < STEPS; t0 += BATCH) {
+            float4 b[BATCH];
+            float vv[BATCH];
+#pragma unroll
+            for (int t = 0; t < BATCH; ++t) {
+                const int cc = __shfl_sync(0xffffffffu, c, (t0 + t) * G + grp);
+                vv[t] = __shfl_sync(0xffffffffu, v, (t0 + t) * G + grp);
+                b[t] = ld_gather4(Bl + (size_t)cc * P);
+            }
+#pragma unroll
+            for (int t = 0; t < BATCH; ++t) {
+                acc.x = fmaf(vv[t], b[t].x, acc.x);
+                acc.y = fmaf(vv[t], b[t].y, acc.y);
+                acc.z = fmaf(vv[t], b[t].z, acc.z);
+                acc.w = fmaf(vv[t], b[t].w, acc.w);
+            }
+        }
+    }
+    if (base < end) {  // tail segment (warp-uniform trip count)
+        const int cnt = (int)(end - base);
+        const bool ok = lane < cnt;
+        const int c = ok ? ld_stream(indices + base + lane) : 0;
+        const float v = ok ? ld_stream(data + base + lane) : 0.f;
+        const int steps = (cnt + G - 1) / G;
+        for (int t = 0; t < steps; ++t) {
+            const int src = t * G + grp;
+            const int cc = __shfl_sync(0xffffffffu, c, src);
+            const float vt = __shfl_sync(0xffffffffu, v, src);
+            if (src < cnt) {
+                const float4 bt = ld_gather4(Bl + (size_t)cc * P);
+                acc.x = fmaf(vt, bt.x, acc.x);
+                acc.y = fmaf(vt, bt.y, acc.y);
+                acc.z = fmaf(vt, bt.z, acc.z);
+                acc.w = fmaf(vt, bt.w, acc.w);
+            }
+        }
+    }
+    // combine the G lane groups (fixed butterfly order: deterministic)
+#pragma unroll
+    for (int off = LPN; off < 32; off <<= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+    if (grp == 0) {
+        float4* dst = reinterpret_cast<float4*>(C_row + sub * 4);
+        if (accumulate) {
+            const float4 o = *dst;
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        *dst = acc;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(kSpmmThreads)
+spmm_csr_rowwarp_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                        const float* __restrict__ data, int64_t n_rows, const float* __restrict__ B,
+                        float* __restrict__ C, int accumulate, unsigned long long* row_counter) {
+    const int lane = threadIdx.x & 31;
+    if (row_counter == nullptr) {
+        const int64_t warp = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
+        const int64_t n_warps = (int64_t)gridDim.x * kSpmmWarps;
+        for (int64_t row = warp; row < n_rows; row += n_warps) {
+            const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+            spmm_row<P>(indices, data, s, e, B, C + (size_t)row * P, accumulate, lane);
+        }
+    } else {
+        // dynamic scheduling: each warp claims the next unprocessed row (rows are issued in
+        // order, so long rows of a skewed matrix cannot pile up on one warp's static list)
+        for (;;) {
+            unsigned long long row = 0;
+            if (lane == 0) row = atomicAdd(row_counter, 1ull);
+            row = __shfl_sync(0xffffffffu, row, 0);
+            if ((int64_t)row >= n_rows) break;
+            const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+            spmm_row<P>(indices, data, s, e, B, C + (size_t)row * P, accumulate, lane);
+        }
+    }
+}
+
+template <int P>
+static int launch_spmm(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                       const float* B, float* C, int accumulate, unsigned long long* row_counter,
+                       cudaStream_t stream) {
+    int64_t want = (n_rows + kSpmmWarps - 1) / kSpmmWarps;
+    int64_t cap = (int64_t)sm_count() * 8;  // 2048 threads / SM
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    spmm_csr_rowwarp_kernel<P><<<grid, kSpmmThreads, 0, stream>>>(indptr, indices, data, n_rows, B, C,
+                                                                   accumulate, row_counter);
+    return check_launch("spmm_csr");
+}
+
+}  // namespace mub
+
+extern "C" int mub_spmm_csr_f32(const int64_t* indptr, const int32_t* indices, const float* data,
+                                int64_t n_rows, int64_t n_cols, const float* B, int32_t ld, float* C,
+                                int32_t accumulate, unsigned long long* row_counter, mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "spmm_csr: negative shape");
+    MUB_REQUIRE(ld == 32 || ld == 64 || ld == 128, "spmm_csr: ld must be 32, 64 or 128 (got %d)", ld);
+    if (n_rows == 0) return 0;
+    MUB_REQUIRE(indptr && B && C, "spmm_csr: null pointer");
+    MUB_REQUIRE((((uintptr_t)B | (uintptr_t)C) & 15) == 0, "spmm_csr: B and C must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (ld) {
+        case 32: return mub::launch_spmm<32>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
+        case 64: return mub::launch_spmm<64>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
+        default: return mub::launch_spmm<128>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
+    }
+}

@@ -1,0 +1,194 @@
+// K1 -- fused CSR TF-IDF for sm_100a (reference arithmetic: muon/_atac/preproc.py:92-119).
+//
+// Two streaming passes over the CSR arrays, both HBM-bound:
+//   reduce : reads indices+values (8 B/nnz fp32), warp-shuffle row sums, column sums by
+//            red.global.add into an L2-resident D-vector (0.8 MB at D=200k)
+//   apply  : reads indices+values, writes values (12 B/nnz fp32); idf[j] is gathered from
+//            a D-vector that stays in L1/L2; 1/r_i computed once per row
+// Algorithmic bytes: 20 B/nnz (fp32) + 8(n+1) + 8D  (SURVEY section 8d).
+//
+// One warp owns one row at a time (coalesced 128 B segments of indices and values, four
+// independent segments in flight per lane); warps take rows round-robin so that
+// consecutive warps stream consecutive memory.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mub {
+
+constexpr int kThreads = 256;
+constexpr int kWarpsPerCta = kThreads / kWarp;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                    const T* __restrict__ data, int64_t n_rows, T* __restrict__ row_sum,
+                    T* __restrict__ col_sum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t row = warp; row < n_rows; row += n_warps) {
+        const int64_t start = __ldg(indptr + row), end = __ldg(indptr + row + 1);
+        T acc = 0;
+        int64_t k = start + lane;
+        // 4 independent coalesced segments in flight per lane
+        for (; k + 96 < end; k += 128) {
+            int c0 = ld_stream(indices + k), c1 = ld_stream(indices + k + 32);
+            int c2 = ld_stream(indices + k + 64), c3 = ld_stream(indices + k + 96);
+            T v0 = ld_stream(data + k), v1 = ld_stream(data + k + 32);
+            T v2 = ld_stream(data + k + 64), v3 = ld_stream(data + k + 96);
+            atomicAdd(col_sum + c0, v0);
+            atomicAdd(col_sum + c1, v1);
+            atomicAdd(col_sum + c2, v2);
+            atomicAdd(col_sum + c3, v3);
+            acc += (v0 + v1) + (v2 + v3);
+        }
+        for (; k < end; k += 32) {
+            int c = ld_stream(indices + k);
+            T v = ld_stream(data + k);
+            atomicAdd(col_sum + c, v);
+            acc += v;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) row_sum[row] = acc;
+    }
+}
+
+template <typename T>
+__global__ void tfidf_idf_kernel(const T* __restrict__ col_sum, int32_t n_cols, T n_obs, uint32_t flags,
+                                 T* __restrict__ idf) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    T v = n_obs / col_sum[j];  // IEEE division; empty column -> inf, never gathered (App. A.4)
+    if (flags & MUB_TFIDF_LOG_IDF) v = log1p(v);
+    idf[j] = v;
+}
+
+template <typename T>
+__device__ __forceinline__ T tfidf_value(T c, T inv_r, T idf, T sf, uint32_t flags) {
+    // association order of the reference: ((1/r) * c) * sf -> log1p -> * idf -> log1p
+    T t;
+    if constexpr (sizeof(T) == 4) {
+        t = __fmul_rn(inv_r, c);
+        if (!(flags & MUB_TFIDF_NO_SCALE)) t = __fmul_rn(t, sf);
+        if (flags & MUB_TFIDF_LOG_TF) t = log1pf(t);
+        t = __fmul_rn(t, idf);
+        if (flags & MUB_TFIDF_LOG_TFIDF) t = log1pf(t);
+    } else {
+        t = __dmul_rn(inv_r, c);
+        if (!(flags & MUB_TFIDF_NO_SCALE)) t = __dmul_rn(t, sf);
+        if (flags & MUB_TFIDF_LOG_TF) t = log1p(t);
+        t = __dmul_rn(t, idf);
+        if (flags & MUB_TFIDF_LOG_TFIDF) t = log1p(t);
+    }
+    // inf * 0 on all-explicit-zero rows: the reference intends 0 there (preproc.py:119)
+    return (t != t) ? T(0) : t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+tfidf_apply_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                   const T* data_in, T* data_out, int64_t n_rows, const T* __restrict__ row_sum,
+                   const T* __restrict__ idf, T sf, uint32_t flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t row = warp; row < n_rows; row += n_warps) {
+        const int64_t start = __ldg(indptr + row), end = __ldg(indptr + row + 1);
+        if (start == end) continue;
+        const T inv_r = T(1) / __ldg(row_sum + row);  // 1.0 / n_peaks, preproc.py:94
+        int64_t k = start + lane;
+        for (; k + 96 < end; k += 128) {
+            int c0 = ld_stream(indices + k), c1 = ld_stream(indices + k + 32);
+            int c2 = ld_stream(indices + k + 64), c3 = ld_stream(indices + k + 96);
+            T v0 = ld_stream_rw(data_in + k), v1 = ld_stream_rw(data_in + k + 32);
+            T v2 = ld_stream_rw(data_in + k + 64), v3 = ld_stream_rw(data_in + k + 96);
+            T i0 = __ldg(idf + c0), i1 = __ldg(idf + c1), i2 = __ldg(idf + c2), i3 = __ldg(idf + c3);
+            st_stream(data_out + k, tfidf_value(v0, inv_r, i0, sf, flags));
+            st_stream(data_out + k + 32, tfidf_value(v1, inv_r, i1, sf, flags));
+            st_stream(data_out + k + 64, tfidf_value(v2, inv_r, i2, sf, flags));
+            st_stream(data_out + k + 96, tfidf_value(v3, inv_r, i3, sf, flags));
+        }
+        for (; k < end; k += 32) {
+            int c = ld_stream(indices + k);
+            T v = ld_stream_rw(data_in + k);
+            st_stream(data_out + k, tfidf_value(v, inv_r, __ldg(idf + c), sf, flags));
+        }
+    }
+}
+
+static int grid_for_rows(int64_t n_rows) {
+    // persistent-style: 8 CTAs of 256 threads per SM (full occupancy), never more warps than rows
+    int64_t want = (n_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    int64_t cap = (int64_t)sm_count() * 8;
+    int64_t g = want < cap ? want : cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <typename T>
+int tfidf_reduce(const int64_t* indptr, const int32_t* indices, const T* data, int64_t n_rows,
+                 int32_t n_cols, T* row_sum, T* col_sum, mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_reduce: negative shape");
+    if (n_rows == 0) return 0;
+    MUB_REQUIRE(indptr && row_sum && col_sum, "tfidf_reduce: null pointer");
+    tfidf_reduce_kernel<T><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
+        indptr, indices, data, n_rows, row_sum, col_sum);
+    return check_launch("tfidf_reduce");
+}
+
+template <typename T>
+int tfidf_idf(const T* col_sum, int32_t n_cols, double n_obs, uint32_t flags, T* idf, mub_stream_t stream) {
+    MUB_REQUIRE(n_cols >= 0, "tfidf_idf: negative n_cols");
+    if (n_cols == 0) return 0;
+    tfidf_idf_kernel<T><<<(n_cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(col_sum, n_cols, (T)n_obs,
+                                                                              flags, idf);
+    return check_launch("tfidf_idf");
+}
+
+template <typename T>
+int tfidf_apply(const int64_t* indptr, const int32_t* indices, const T* data_in, T* data_out,
+                int64_t n_rows, int32_t n_cols, const T* row_sum, const T* idf, T sf, uint32_t flags,
+                mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_apply: negative shape");
+    MUB_REQUIRE(!((flags & MUB_TFIDF_LOG_TFIDF) && (flags & (MUB_TFIDF_LOG_TF | MUB_TFIDF_LOG_IDF))),
+                "tfidf_apply: LOG_TFIDF excludes LOG_TF/LOG_IDF (preproc.py:69-73)");
+    if (n_rows == 0) return 0;
+    tfidf_apply_kernel<T><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
+        indptr, indices, data_in, data_out, n_rows, row_sum, idf, sf, flags);
+    return check_launch("tfidf_apply");
+}
+
+}  // namespace mub
+
+extern "C" {
+
+int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                         int32_t n_cols, float* row_sum, float* col_sum, mub_stream_t stream) {
+    return mub::tfidf_reduce<float>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, stream);
+}
+int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const double* data, int64_t n_rows,
+                         int32_t n_cols, double* row_sum, double* col_sum, mub_stream_t stream) {
+    return mub::tfidf_reduce<double>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, stream);
+}
+int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags, float* idf,
+                      mub_stream_t stream) {
+    return mub::tfidf_idf<float>(col_sum, n_cols, n_obs_total, flags, idf, stream);
+}
+int mub_tfidf_idf_f64(const double* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags, double* idf,
+                      mub_stream_t stream) {
+    return mub::tfidf_idf<double>(col_sum, n_cols, n_obs_total, flags, idf, stream);
+}
+int mub_tfidf_apply_f32(const int64_t* indptr, const int32_t* indices, const float* data_in, float* data_out,
+                        int64_t n_rows, int32_t n_cols, const float* row_sum, const float* idf,
+                        float scale_factor, uint32_t flags, mub_stream_t stream) {
+    return mub::tfidf_apply<float>(indptr, indices, data_in, data_out, n_rows, n_cols, row_sum, idf,
+                                   scale_factor, flags, stream);
+}
+int mub_tfidf_apply_f64(const int64_t* indptr, const int32_t* indices, const double* data_in,
+                        double* data_out, int64_t n_rows, int32_t n_cols, const double* row_sum,
+                        const double* idf, double scale_factor, uint32_t flags, mub_stream_t stream) {
+    return mub::tfidf_apply<double>(indptr, indices, data_in, data_out, n_rows, n_cols, row_sum, idf,
+                                    scale_factor, flags, stream);
+}
+
+}  // extern "C"

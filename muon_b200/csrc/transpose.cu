@@ -1,0 +1,97 @@
+// CSR -> CSR-of-transpose (one-time per matrix) so that A^T * Y is a row-gather SpMM too.
+// scipy reaches the same effect through csc_matvec on the CSR arrays (_svds.py:447 via
+// muon/_atac/tools.py:53); on the GPU a scatter-add formulation would need ld atomics per
+// non-zero, so the transposed copy is built once per LSI/MOFA call instead.
+//
+// count : histogram of column indices (int64 counters, one red per non-zero, L2-resident)
+// fill  : warp per source row; each non-zero claims a slot in its column with an atomic
+//         cursor (seeded from the scanned histogram) and writes (row, value) there.
+#include "common.cuh"
+
+namespace mub {
+
+__global__ void __launch_bounds__(256)
+transpose_count_kernel(const int32_t* __restrict__ indices, int64_t nnz, int head,
+                       unsigned long long* t_count) {
+    // `head` leading elements (<4) precede the first 16-byte boundary: scalar path
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < head) atomicAdd(t_count + 1 + ld_stream(indices + i), 1ull);
+    indices += head;
+    nnz -= head;
+    const int64_t nvec = nnz >> 2;
+    const int4* v = reinterpret_cast<const int4*>(indices);
+    for (int64_t k = i; k < nvec; k += stride) {
+        const int4 c = ld_stream4(v + k);
+        atomicAdd(t_count + 1 + c.x, 1ull);
+        atomicAdd(t_count + 1 + c.y, 1ull);
+        atomicAdd(t_count + 1 + c.z, 1ull);
+        atomicAdd(t_count + 1 + c.w, 1ull);
+    }
+    for (int64_t k = (nvec << 2) + i; k < nnz; k += stride) atomicAdd(t_count + 1 + ld_stream(indices + k), 1ull);
+}
+
+__global__ void copy_i64_kernel(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256)
+transpose_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                      const float* __restrict__ data, int64_t n_rows, int64_t row_offset,
+                      unsigned long long* cursor, int32_t* __restrict__ t_indices, float* __restrict__ t_data) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t row = warp; row < n_rows; row += n_warps) {
+        const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        const int32_t r = (int32_t)(row + row_offset);
+        for (int64_t k = s + lane; k < e; k += 32) {
+            const int c = ld_stream(indices + k);
+            const float v = ld_stream(data + k);
+            const unsigned long long slot = atomicAdd(cursor + c, 1ull);
+            t_indices[slot] = r;
+            t_data[slot] = v;
+        }
+    }
+}
+
+}  // namespace mub
+
+extern "C" {
+
+int mub_csr_transpose_count(const int32_t* indices, int64_t nnz, int32_t n_cols, int64_t* t_count,
+                            mub_stream_t stream) {
+    MUB_REQUIRE(nnz >= 0 && n_cols >= 0, "transpose_count: negative size");
+    if (nnz == 0) return 0;
+    MUB_REQUIRE(indices && t_count, "transpose_count: null pointer");
+    MUB_REQUIRE(((uintptr_t)indices & 3) == 0, "transpose_count: indices must be 4-byte aligned");
+    int head = (int)(((16 - ((uintptr_t)indices & 15)) & 15) >> 2);
+    if (head > nnz) head = (int)nnz;
+    int64_t want = (nnz / 4 + 255) / 256;
+    int64_t cap = (int64_t)mub::sm_count() * 8;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    mub::transpose_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(indices, nnz, head,
+                                                                      (unsigned long long*)t_count);
+    return mub::check_launch("transpose_count");
+}
+
+int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                           int32_t n_cols, int64_t row_offset, const int64_t* t_indptr, int64_t* cursor,
+                           int32_t* t_indices, float* t_data, mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "transpose_fill: negative shape");
+    if (n_rows == 0 || n_cols == 0) return 0;
+    MUB_REQUIRE(indptr && t_indptr && cursor && t_indices && t_data, "transpose_fill: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    mub::copy_i64_kernel<<<(n_cols + 255) / 256, 256, 0, s>>>(t_indptr, cursor, n_cols);
+    int64_t want = (n_rows + 7) / 8;
+    int64_t cap = (int64_t)mub::sm_count() * 8;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    mub::transpose_fill_kernel<<<grid, 256, 0, s>>>(indptr, indices, data, n_rows, row_offset,
+                                                   (unsigned long long*)cursor, t_indices, t_data);
+    return mub::check_launch("transpose_fill");
+}
+
+}  // extern "C"

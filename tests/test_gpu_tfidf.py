@@ -1,0 +1,150 @@
+"""GPU parity: CUDA TF-IDF (through the C ABI) vs the CPU oracle and the reference's goldens."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import muon_b200 as mu
+from conftest import golden_csr, load_golden
+from muon_b200._containers import SimpleAnnData, SimpleMuData
+from muon_b200._synth import generate_host
+from oracle.tfidf_ref import tfidf_closed_form, tfidf_ref
+
+pytestmark = pytest.mark.gpu
+
+# float32 log1p on the device vs numpy differs by <= 2 ulp; sums of integer counts are exact
+RTOL32, RTOL64 = 1e-6, 1e-12
+
+
+def _canon(m):
+    m = sp.csr_matrix(m)
+    m.sort_indices()
+    return m
+
+
+def _assert_parity(got, ref, rtol):
+    got, ref = _canon(got), _canon(ref)
+    np.testing.assert_array_equal(got.indptr, ref.indptr)      # bit-exact pattern
+    np.testing.assert_array_equal(got.indices, ref.indices)
+    assert got.dtype == ref.dtype
+    np.testing.assert_allclose(got.data, ref.data, rtol=rtol, atol=0)
+
+
+def test_reference_kat_dense(cuda):
+    # reference tests/test_atac_preproc.py:16-20
+    np.random.seed(2020)
+    x = np.abs(np.random.normal(size=(4, 5)))
+    adata = SimpleAnnData(x.copy())
+    assert mu.atac.pp.tfidf(adata, log_tf=True, log_idf=True) is None
+    assert sp.isspmatrix_csr(adata.X)
+    assert "%.3f" % adata.X[0, 0] == "4.659"
+    assert "%.3f" % adata.X[3, 0] == "4.770"
+    z = load_golden("tfidf_dense.npz")
+    np.testing.assert_allclose(adata.X.toarray(), z["out"], rtol=RTOL64)
+
+
+def test_reference_kat_view_copy_inplace_layers(cuda):
+    np.random.seed(2020)
+    x = np.abs(np.random.normal(size=(4, 5)))
+    base = SimpleAnnData(x.copy())
+    view = base[:, :]                                   # test_tfidf_view
+    mu.atac.pp.tfidf(view)
+    assert "%.3f" % view.X[0, 0] == "4.659" and not view.is_view
+    adata = base.copy()                                 # test_tfidf_copy
+    orig = adata.X[0, 0]
+    cp = mu.atac.pp.tfidf(adata, copy=True)
+    assert adata.X[0, 0] == orig and "%.3f" % cp.X[0, 0] == "4.659"
+    res = mu.atac.pp.tfidf(adata, inplace=False)        # test_tfidf_inplace
+    assert adata.X[0, 0] == orig and "%.3f" % res[0, 0] == "4.659"
+    mu.atac.pp.tfidf(adata, to_layer="new")             # test_tfidf_to_layer
+    assert adata.X[0, 0] == orig and "%.3f" % adata.layers["new"][0, 0] == "4.659"
+    with pytest.warns(UserWarning):
+        mu.atac.pp.tfidf(adata, to_layer="new")
+    a2 = base.copy()                                    # test_tfidf_from_layer
+    a2.layers["counts"] = a2.X.copy() + 1
+    a2.X = None
+    mu.atac.pp.tfidf(a2, from_layer="counts")
+    assert "%.3f" % a2.X[0, 0] == "2.856"
+    md = SimpleMuData({"atac": base.copy(), "rna": SimpleAnnData(np.ones((4, 2)))})
+    mu.atac.pp.tfidf(md)
+    assert "%.3f" % md.mod["atac"].X[0, 0] == "4.659"
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("default", {}), ("nolog_tf", {"log_tf": False}), ("nolog_idf", {"log_idf": False}),
+    ("log_tfidf", {"log_tf": False, "log_idf": False, "log_tfidf": True}),
+    ("noscale", {"scale_factor": 1}), ("sf100", {"scale_factor": 100.0})])
+def test_reference_kat_sparse_all_flags(cuda, name, kw):
+    z = load_golden("tfidf_sparse.npz")
+    adata = SimpleAnnData(golden_csr(z, "x"))
+    mu.atac.pp.tfidf(adata, **kw)
+    if name == "default":
+        assert "%.3f" % adata.X[10, 9] == "18.749" and "%.3f" % adata.X[50, 5] == "0.000"
+    _assert_parity(adata.X, golden_csr(z, f"out_{name}"), RTOL64)
+
+
+def test_float32_synth_vs_unmodified_reference(cuda):
+    z = load_golden("tfidf_synth.npz")
+    adata = SimpleAnnData(golden_csr(z, "x"))
+    mu.atac.pp.tfidf(adata)
+    _assert_parity(adata.X, golden_csr(z, "out"), RTOL32)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(np.float32, RTOL32), (np.float64, RTOL64)])
+def test_config0_shape_vs_oracle(cuda, dtype, rtol):
+    # BASELINE.json configs[0]: 10k x 30k, 5 % -- correctness only
+    X = generate_host(2000, 30000, 0.05, n_topics=16, seed=0).astype(dtype)
+    ref = tfidf_ref(X)
+    adata = SimpleAnnData(X.copy())
+    mu.atac.pp.tfidf(adata)
+    _assert_parity(adata.X, ref, rtol)
+    vals, rs, cs = tfidf_closed_form(X.indptr, X.indices, X.data, *X.shape)
+    np.testing.assert_allclose(_canon(adata.X).data, vals, rtol=rtol)
+
+
+def test_integer_counts_and_edge_cases(cuda):
+    rng = np.random.default_rng(0)
+    X = sp.random(200, 50, 0.1, format="csr", random_state=1)
+    X.data = rng.integers(1, 5, X.nnz).astype(np.int64)
+    X = sp.csr_matrix(X)
+    lil = X.tolil()
+    lil[3, :] = 0          # empty row
+    lil[:, 7] = 0          # empty column
+    X = lil.tocsr().astype(np.int64)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = tfidf_ref(X)
+    adata = SimpleAnnData(X.copy())
+    mu.atac.pp.tfidf(adata)
+    assert adata.X.dtype == np.float64          # integer counts -> float64
+    _assert_parity(adata.X, ref, RTOL64)
+    # explicit zeros and duplicates are canonicalised like the reference's matmul does (App. A.3)
+    Xd = sp.csr_matrix((np.array([1.0, 2.0, 0.0, 3.0]), np.array([0, 0, 1, 2]), np.array([0, 3, 4])), shape=(2, 3))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = tfidf_ref(Xd)
+    got = mu.atac.pp.tfidf(SimpleAnnData(Xd.copy()), inplace=False)
+    _assert_parity(got, ref, RTOL64)
+    # empty matrix
+    E = sp.csr_matrix((5, 4), dtype=np.float32)
+    got = mu.atac.pp.tfidf(SimpleAnnData(E), inplace=False)
+    assert got.nnz == 0 and got.shape == (5, 4)
+
+
+def test_device_resident_and_properties(cuda):
+    """Size-independent properties at a larger shape: pattern untouched, positivity, scale
+    invariance of TF under duplication of cells, resident path == host path."""
+    X = generate_host(4000, 5000, 0.03, n_topics=8, seed=2)
+    dev = mu.DeviceCSR.from_scipy(X)
+    ad = SimpleAnnData(dev)
+    mu.atac.pp.tfidf(ad)
+    assert isinstance(ad.X, mu.DeviceCSR) and ad.X.data.data_ptr() != dev.data.data_ptr()
+    out = ad.X.get()
+    host = mu.atac.pp.tfidf(SimpleAnnData(X.copy()), inplace=False)
+    np.testing.assert_array_equal(out.indices, X.indices)
+    np.testing.assert_array_equal(out.data, host.data)
+    assert np.all(out.data > 0) and np.all(np.isfinite(out.data))
+    # stacking the matrix on itself doubles N and every column sum: idf unchanged -> same values
+    X2 = sp.vstack([X, X]).tocsr()
+    out2 = mu.atac.pp.tfidf(SimpleAnnData(X2), inplace=False)
+    np.testing.assert_allclose(out2[:4000].data, out.data, rtol=1e-6)

@@ -1,0 +1,129 @@
+"""CPU: host-side logic above the C ABI -- containers, argument checking, the block
+Golub-Kahan driver (with a scipy operator injected by the test; the product wires CUDA)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import muon_b200 as mu
+from conftest import golden_csr, load_golden
+from muon_b200._containers import SimpleAnnData, SimpleMuData, view_to_actual
+from muon_b200._lsi import truncated_svd
+from muon_b200._synth import generate_host, make_tables
+from oracle.lsi_ref import compare_lsi, lsi_ref
+from oracle.tfidf_ref import tfidf_ref
+
+
+class ScipyOperator:
+    """Test-only stand-in for CsrOperator (same protocol: av, aty, gram)."""
+
+    def __init__(self, A):
+        self.A = sp.csr_matrix(A).astype(np.float32)
+        self.At = self.A.T.tocsr()
+        self.n_local, self.d = self.A.shape
+        self.n_total = self.n_local
+        self.device = torch.device("cpu")
+
+    def av(self, V):
+        return torch.from_numpy(self.A @ V.numpy())
+
+    def aty(self, Y):
+        return torch.from_numpy(self.At @ Y.numpy())
+
+    def gram(self, Y, l):
+        y = Y[:, :l].double()
+        return y.T @ y
+
+
+def test_containers_view_copy_slots():
+    x = np.arange(20, dtype=float).reshape(4, 5)
+    ad = SimpleAnnData(x)
+    v = ad[:, :]
+    assert v.is_view
+    view_to_actual(v)
+    assert not v.is_view and v.X is not ad.X
+    c = ad.copy()
+    c.X[0, 0] = -1
+    assert ad.X[0, 0] == 0
+    with pytest.raises(ValueError):
+        ad.X = np.zeros((3, 3))
+    md = SimpleMuData({"atac": ad, "rna": SimpleAnnData(np.ones((4, 3)))})
+    assert md.n_obs == 4 and md.n_vars == 8 and "atac" in md.mod
+
+
+def test_tfidf_argument_errors_match_reference():
+    # muon/_atac/preproc.py:62-79 -- raised before any device work
+    ad = SimpleAnnData(np.ones((3, 3)))
+    with pytest.raises(TypeError):
+        mu.atac.pp.tfidf(np.ones((3, 3)))
+    with pytest.raises(TypeError):
+        mu.atac.pp.tfidf(SimpleMuData({"rna": ad}))
+    with pytest.raises(AttributeError):
+        mu.atac.pp.tfidf(ad, log_tfidf=True)
+    with pytest.raises(ValueError):
+        mu.atac.pp.tfidf(ad, copy=True, inplace=False)
+    with pytest.raises(ValueError):
+        mu.atac.pp.tfidf(ad, to_layer="x", inplace=False)
+    with pytest.raises(TypeError):
+        mu.atac.tl.lsi(np.ones((3, 3)))
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from muon_b200._lib import MuonB200Error
+    ad = SimpleAnnData(sp.random(20, 10, 0.3, format="csr", random_state=0))
+    with pytest.raises(MuonB200Error):
+        mu.atac.pp.tfidf(ad)
+    with pytest.raises(MuonB200Error):
+        mu.atac.tl.lsi(ad, n_comps=3)
+
+
+@pytest.mark.parametrize("k,P", [(8, 32), (20, 32), (30, 64)])
+def test_block_lanczos_matches_svds(k, P):
+    X = tfidf_ref(generate_host(1500, 1200, 0.05, n_topics=12, seed=3)).astype(np.float32)
+    ref = lsi_ref(X, k + 1, dtype=np.float64)
+    s_next = ref["svalues"][k]
+    ref = {"svalues": ref["svalues"][:k], "U": ref["U"][:, :k], "LSI": ref["LSI"][:, :k]}
+    U, s, V, info = truncated_svd(ScipyOperator(X), k, P, tol=1e-5)
+    assert info.converged
+    out = compare_lsi({"svalues": s.numpy(), "U": U.numpy(), "LSI": V.numpy()}, ref, rtol=1e-4, s_next=s_next)
+    assert out["sigma_rel"] < 1e-5
+
+
+def test_block_lanczos_small_dims_and_restart():
+    # d smaller than the kernel width, and a basis cap that forces a restart
+    X = sp.random(300, 20, 0.4, format="csr", random_state=1, dtype=np.float32)
+    ref = lsi_ref(X, 5, dtype=np.float64)
+    U, s, V, info = truncated_svd(ScipyOperator(X), 5, 32)
+    np.testing.assert_allclose(s.numpy(), ref["svalues"], rtol=1e-5)
+    X = tfidf_ref(generate_host(800, 900, 0.05, n_topics=8, seed=4)).astype(np.float32)
+    ref = lsi_ref(X, 6, dtype=np.float64)
+    U, s, V, info = truncated_svd(ScipyOperator(X), 6, 32, max_basis=96, max_restarts=8)
+    assert info.restarts >= 1
+    np.testing.assert_allclose(s.numpy(), ref["svalues"], rtol=1e-4)
+
+
+def test_oracle_lsi_matches_unmodified_reference():
+    z = load_golden("lsi_synth.npz")
+    X = golden_csr(z, "x")
+    r = lsi_ref(X, 8)
+    np.testing.assert_allclose(r["stdev"], z["stdev"], rtol=1e-10)
+    got = {"svalues": r["stdev"], "U": r["U"], "LSI": r["LSI"]}
+    ref = {"svalues": z["stdev"], "U": z["U"], "LSI": z["LSI"]}
+    compare_lsi(got, ref, rtol=1e-8)
+    emb = r["X_lsi"] * np.sign((r["X_lsi"] * z["X_lsi"]).sum(0))
+    np.testing.assert_allclose(emb, z["X_lsi"], rtol=0, atol=1e-7)
+
+
+def test_synth_generator_is_shard_consistent():
+    tb = make_tables(700, 0.05, n_topics=5, seed=9)
+    full = generate_host(120, 700, 0.05, tables=tb)
+    a = generate_host(50, 700, 0.05, tables=tb, row0=0)
+    b = generate_host(70, 700, 0.05, tables=tb, row0=50)
+    stacked = sp.vstack([a, b]).tocsr()
+    np.testing.assert_array_equal(full.indptr, stacked.indptr)
+    np.testing.assert_array_equal(full.indices, stacked.indices)
+    np.testing.assert_array_equal(full.data, stacked.data)
+    assert abs(full.nnz / (120 * 700) - 0.05) < 0.01
+    assert set(np.unique(full.data)) <= {1.0, 2.0, 3.0, 4.0, 5.0}
