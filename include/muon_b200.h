@@ -47,13 +47,16 @@ int mub_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
 /* ---- TF-IDF (muon/_atac/preproc.py:92-119) -------------------------------------------- */
 /* pass 1: row_sum[i] = sum_j c_ij (preproc.py:93);  col_sum[j] += sum_i c_ij (preproc.py:106).
  * row_sum is overwritten, col_sum is ACCUMULATED (zero it first; allreduce it across
- * cell shards before pass 2). */
+ * cell shards before pass 2).  status (optional int32 word, zeroed by the caller) receives
+ * bit0 if some row's column indices are not strictly increasing (unsorted or duplicate entries)
+ * and bit1 if an explicit zero is stored: such input must be canonicalised first to reproduce
+ * the reference's output pattern (scipy's matmul merges duplicates and drops zeros). */
 int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const float* data,
                          int64_t n_rows, int32_t n_cols, float* row_sum, float* col_sum,
-                         mub_stream_t stream);
+                         int32_t* status, mub_stream_t stream);
 int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const double* data,
                          int64_t n_rows, int32_t n_cols, double* row_sum, double* col_sum,
-                         mub_stream_t stream);
+                         int32_t* status, mub_stream_t stream);
 /* idf[j] = n_obs_total / col_sum[j], log1p if MUB_TFIDF_LOG_IDF (preproc.py:106-108) */
 int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags,
                       float* idf, mub_stream_t stream);
@@ -84,8 +87,8 @@ int mub_spmm_csr_f32(const int64_t* indptr, const int32_t* indices, const float*
  * Step 1 counts entries per column into t_count[n_cols+1] (int64, zeroed by caller, slot 0 unused
  * so that an inclusive scan of t_count is t_indptr); the caller scans (any device scan), then
  * step 2 scatters.  cursor: int64[n_cols] scratch, overwritten.  Entry order inside a
- * transposed row is not deterministic (atomic slot claim) unless `sorted` != 0, in which case a
- * per-row insertion pass restores ascending order. */
+ * transposed row is not deterministic (atomic slot claim): sums over it differ run to run in
+ * the last fp32 bits. */
 int mub_csr_transpose_count(const int32_t* indices, int64_t nnz, int32_t n_cols, int64_t* t_count,
                             mub_stream_t stream);
 int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const float* data,

@@ -34,25 +34,30 @@ _STAGE_BYTES = 256 << 20
 
 
 def to_device(arr, device, dtype=None) -> torch.Tensor:
-    """Host array -> device tensor.  Pinned inputs go in one async copy; pageable inputs are
-    staged through two pinned buffers so that the PCIe copy overlaps the host memcpy."""
+    """Host array -> device tensor of numpy dtype ``dtype`` (default: unchanged).
+
+    Pinned inputs go in one async copy.  Pageable inputs are staged through two pinned buffers
+    so the PCIe copy of one chunk overlaps the host memcpy of the next; a dtype change
+    (e.g. scipy's int64 indices -> int32) happens on the device per chunk, never on the host."""
     if isinstance(arr, torch.Tensor):
         t = arr
     else:
         a = np.ascontiguousarray(arr)
-        if dtype is not None and a.dtype != dtype:
-            a = a.astype(dtype)
         if not a.flags.writeable:
             a = a.copy()
         t = torch.from_numpy(a)
+    tgt = t.dtype if dtype is None else getattr(torch, np.dtype(dtype).name)
     if t.device.type == "cuda":
-        return t
-    if t.is_pinned() or t.numel() * t.element_size() <= _STAGE_BYTES:
-        return t.to(device, non_blocking=True)
-    out = torch.empty(t.shape, dtype=t.dtype, device=device)
+        return t if t.dtype == tgt else t.to(tgt)
+    nbytes = t.numel() * t.element_size()
+    if t.is_pinned() or nbytes <= _STAGE_BYTES:
+        out = t.to(device, non_blocking=True)
+        return out if out.dtype == tgt else out.to(tgt)
+    out = torch.empty(t.shape, dtype=tgt, device=device)
     flat_src, flat_dst = t.reshape(-1), out.reshape(-1)
     step = _STAGE_BYTES // t.element_size()
     stage = [torch.empty(step, dtype=t.dtype).pin_memory() for _ in range(2)]
+    dstage = [torch.empty(step, dtype=t.dtype, device=device) for _ in range(2)] if tgt != t.dtype else None
     events = [None, None]
     for i, off in enumerate(range(0, flat_src.numel(), step)):
         s = stage[i & 1]
@@ -60,11 +65,46 @@ def to_device(arr, device, dtype=None) -> torch.Tensor:
             events[i & 1].synchronize()
         n = min(step, flat_src.numel() - off)
         s[:n].copy_(flat_src[off:off + n])
-        flat_dst[off:off + n].copy_(s[:n], non_blocking=True)
+        if dstage is None:
+            flat_dst[off:off + n].copy_(s[:n], non_blocking=True)
+        else:
+            dstage[i & 1][:n].copy_(s[:n], non_blocking=True)
+            flat_dst[off:off + n].copy_(dstage[i & 1][:n])
         ev = torch.cuda.Event()
         ev.record()
         events[i & 1] = ev
     torch.cuda.current_stream().synchronize()
+    return out
+
+
+def to_host(t: torch.Tensor, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """Device tensor -> numpy array, staged through pinned buffers for large transfers."""
+    nbytes = t.numel() * t.element_size()
+    if out is None:
+        out = np.empty(tuple(t.shape), dtype=getattr(np, str(t.dtype).split(".")[1]))
+    dst = torch.from_numpy(out).reshape(-1)
+    src = t.reshape(-1)
+    if nbytes <= _STAGE_BYTES or dst.is_pinned():
+        dst.copy_(src)
+        return out
+    step = _STAGE_BYTES // t.element_size()
+    stage = [torch.empty(step, dtype=t.dtype).pin_memory() for _ in range(2)]
+    events = [None, None]
+    pending = [None, None]
+    chunks = list(range(0, src.numel(), step))
+    for i, off in enumerate(chunks + [None]):
+        if off is not None:
+            n = min(step, src.numel() - off)
+            stage[i & 1][:n].copy_(src[off:off + n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            events[i & 1], pending[i & 1] = ev, (off, n)
+        j = (i - 1) & 1
+        if i >= 1 and pending[j] is not None:
+            events[j].synchronize()
+            o, n = pending[j]
+            dst[o:o + n].copy_(stage[j][:n])
+            pending[j] = None
     return out
 
 
@@ -76,14 +116,28 @@ class DeviceCSR:
     ``row0``/``n_total`` describe a cell shard of a larger matrix (one shard per rank).
     """
 
-    def __init__(self, indptr, indices, data, shape, row0: int = 0, n_total: Optional[int] = None):
+    def __init__(self, indptr, indices, data, shape, row0: int = 0, n_total: Optional[int] = None,
+                 sorted_indices: bool = True):
         self.indptr, self.indices, self.data = indptr, indices, data
+        self.sorted_indices = sorted_indices
         self.shape = (int(shape[0]), int(shape[1]))
         self.row0 = int(row0)
-        self.n_total = int(n_total) if n_total is not None else self.shape[0]
+        self._n_total = int(n_total) if n_total is not None else None
         self._t = None  # cached transpose (DeviceCSR of A^T), invalidated when data is rebound
         assert indptr.dtype == torch.int64 and indices.dtype == torch.int32
         assert indptr.numel() == self.shape[0] + 1
+
+    @property
+    def n_total(self) -> int:
+        """Number of cells of the whole (possibly sharded) matrix: explicit, else the sum of the
+        shard heights over the process group, else the local height."""
+        if self._n_total is None:
+            if _dist.is_distributed():
+                t = torch.tensor([self.shape[0]], dtype=torch.int64, device=self.data.device)
+                self._n_total = int(_dist.all_reduce_sum_(t)[0])
+            else:
+                self._n_total = self.shape[0]
+        return self._n_total
 
     # -- scipy-ish surface -------------------------------------------------------------
     @property
@@ -100,7 +154,8 @@ class DeviceCSR:
 
     def with_data(self, data) -> "DeviceCSR":
         """Same sparsity pattern (shared index tensors), new values."""
-        return DeviceCSR(self.indptr, self.indices, data, self.shape, self.row0, self.n_total)
+        return DeviceCSR(self.indptr, self.indices, data, self.shape, self.row0, self._n_total,
+                         self.sorted_indices)
 
     def copy(self) -> "DeviceCSR":
         return self.with_data(self.data.clone())
@@ -120,13 +175,13 @@ class DeviceCSR:
         """Download as scipy.sparse.csr_matrix.  Host index arrays may be passed to be reused
         (the sparsity pattern is never modified on the device)."""
         import scipy.sparse as sp
-        data = self.data.cpu().numpy()
-        indptr = self.indptr.cpu().numpy() if indptr_host is None else indptr_host
-        indices = self.indices.cpu().numpy() if indices_host is None else indices_host
+        data = to_host(self.data)
+        indptr = to_host(self.indptr) if indptr_host is None else indptr_host
+        indices = to_host(self.indices) if indices_host is None else indices_host
         if self.nnz < 2**31 - 1 and indptr.dtype != np.int32:
             indptr = indptr.astype(np.int32)
         m = sp.csr_matrix((data, indices, indptr), shape=self.shape, copy=False)
-        m.has_sorted_indices = True
+        m.has_sorted_indices = bool(self.sorted_indices)
         return m
 
     # -- transpose (cached) --------------------------------------------------------------
@@ -138,7 +193,7 @@ class DeviceCSR:
 
 # ------------------------------------------------------------------------------------------
 def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=1e4,
-              inplace_values=False) -> DeviceCSR:
+              inplace_values=False, check_canonical=False) -> Optional[DeviceCSR]:
     """K1: two fused passes (reduce, apply).  Column sums are allreduced across cell shards
     (muon/_atac/preproc.py:92-119; multi-GPU plan SURVEY section 8e)."""
     require_cuda()
@@ -152,7 +207,11 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
     row_sum = torch.empty(n, dtype=dt, device=dev)
     col_sum = torch.zeros(d, dtype=dt, device=dev)
     st = stream_ptr()
-    call(f"mub_tfidf_reduce_{sfx}", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(row_sum), ptr(col_sum), st)
+    status = torch.zeros(1, dtype=torch.int32, device=dev) if check_canonical else None
+    call(f"mub_tfidf_reduce_{sfx}", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(row_sum), ptr(col_sum),
+         ptr(status), st)
+    if check_canonical and int(status[0]) != 0:
+        return None  # caller canonicalises (duplicates / explicit zeros / unsorted rows) and retries
     _dist.all_reduce_sum_(col_sum)
     idf = torch.empty(d, dtype=dt, device=dev)
     call(f"mub_tfidf_idf_{sfx}", ptr(col_sum), d, float(A.n_total), flags, ptr(idf), st)
@@ -179,7 +238,7 @@ def csr_transpose(A: DeviceCSR) -> DeviceCSR:
     t_data = torch.empty(A.nnz, dtype=torch.float32, device=dev)
     call("mub_csr_transpose_fill", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, 0, ptr(t_indptr), ptr(cursor),
          ptr(t_indices), ptr(t_data), st)
-    return DeviceCSR(t_indptr, t_indices, t_data, (d, n))
+    return DeviceCSR(t_indptr, t_indices, t_data, (d, n), n_total=d, sorted_indices=False)
 
 
 def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False,
@@ -210,3 +269,39 @@ def gram(Y: torch.Tensor, l: Optional[int] = None, weights: Optional[torch.Tenso
     if reduce:
         _dist.all_reduce_sum_(G)
     return G
+
+
+# ------------------------------------------------------------------------------------------
+# Host matrices produced by tfidf() keep a handle to their device twin so that a following
+# lsi() on the same AnnData does not pay the PCIe upload again.  The handle is validated
+# against the host values (sampled fingerprint) before use, so editing X on the host is safe.
+_RESIDENT_ATTR = "_mub_resident"
+
+
+def remember_resident(host_matrix, dev: "DeviceCSR"):
+    try:
+        setattr(host_matrix, _RESIDENT_ATTR, dev)
+    except Exception:
+        pass
+
+
+def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
+    dev = getattr(host_matrix, _RESIDENT_ATTR, None)
+    if dev is None or not isinstance(dev, DeviceCSR):
+        return None
+    try:
+        if tuple(dev.shape) != tuple(host_matrix.shape) or dev.nnz != host_matrix.nnz:
+            return None
+        if host_matrix.data.dtype != np.float32 or dev.data.dtype != torch.float32:
+            return None
+        nnz = dev.nnz
+        if nnz:
+            pos = np.unique(np.linspace(0, nnz - 1, num=min(nnz, 4096), dtype=np.int64))
+            idx = torch.from_numpy(pos).to(dev.data.device)
+            if not np.array_equal(dev.data[idx].cpu().numpy(), host_matrix.data[pos]):
+                return None
+            if not np.array_equal(dev.indices[idx].cpu().numpy(), np.asarray(host_matrix.indices[pos], dtype=np.int32)):
+                return None
+        return dev
+    except Exception:
+        return None

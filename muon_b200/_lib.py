@@ -24,8 +24,8 @@ i64, i32, u32, u64, f32, f64, vp = C.c_int64, C.c_int32, C.c_uint32, C.c_uint64,
 SIGNATURES = {
     "mub_version": [],
     "mub_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)],
-    "mub_tfidf_reduce_f32": [vp, vp, vp, i64, i32, vp, vp, vp],
-    "mub_tfidf_reduce_f64": [vp, vp, vp, i64, i32, vp, vp, vp],
+    "mub_tfidf_reduce_f32": [vp, vp, vp, i64, i32, vp, vp, vp, vp],
+    "mub_tfidf_reduce_f64": [vp, vp, vp, i64, i32, vp, vp, vp, vp],
     "mub_tfidf_idf_f32": [vp, i32, f64, u32, vp, vp],
     "mub_tfidf_idf_f64": [vp, i32, f64, u32, vp, vp],
     "mub_tfidf_apply_f32": [vp, vp, vp, vp, i64, i32, vp, vp, f32, u32, vp],
@@ -75,10 +75,26 @@ def load():
     return _lib
 
 
+# kernels launched per successful call (for the benchmark's gpu_launches claim)
+KERNELS_PER_CALL = {"mub_csr_transpose_fill": 2, "mub_gram_f32": 2, "mub_version": 0, "mub_device_info": 0}
+LAUNCHES = 0          # running count of kernels launched through this binding
+PROFILE = None        # None, or dict name -> list[(start_event, end_event)] filled by call()
+
+
 def call(name: str, *args):
     """Call an int-returning entry point and raise MuonB200Error with mub_last_error() on failure."""
+    global LAUNCHES
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.mub_last_error()
         raise MuonB200Error(f"{name} failed (rc={rc}): {msg.decode() if msg else '?'}")

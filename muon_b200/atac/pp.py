@@ -9,16 +9,13 @@ import numpy as np
 from .._containers import is_anndata, is_mudata, view_to_actual
 
 
-def _canonical_csr(counts):
+def _canonical_csr(X):
     """Host-side canonicalisation matching what scipy's matmul does to the reference's output
     pattern: duplicates summed, explicit zeros dropped, indices sorted."""
-    import scipy.sparse as sp
-    X = counts if sp.isspmatrix_csr(counts) else sp.csr_matrix(counts)
-    if not X.has_canonical_format or (X.nnz and np.any(X.data == 0)):
-        X = X.copy()
-        X.sum_duplicates()
-        X.eliminate_zeros()
-        X.sort_indices()
+    X = X.copy()
+    X.sum_duplicates()
+    X.eliminate_zeros()
+    X.sort_indices()
     return X
 
 
@@ -73,13 +70,22 @@ def tfidf(
     if isinstance(counts, _device.DeviceCSR):
         res = _device.tfidf_csr(counts, log_tf, log_idf, log_tfidf, scale_factor)
     else:
-        X = _canonical_csr(counts)
-        if X.dtype not in (np.float32, np.float64):
-            X = X.astype(np.float64)  # integer counts -> float64, SURVEY App. A.2
-        dev = _device.DeviceCSR.from_scipy(X)
-        out = _device.tfidf_csr(dev, log_tf, log_idf, log_tfidf, scale_factor, inplace_values=True)
+        import scipy.sparse as sp
+        X = counts if sp.isspmatrix_csr(counts) else sp.csr_matrix(counts)
+        cdt = X.dtype if X.dtype in (np.float32, np.float64) else np.float64  # ints -> f64, App. A.2
+        out = None
+        for attempt in range(2):
+            dev = _device.DeviceCSR.from_scipy(X, dtype=cdt)
+            # the kernel itself verifies canonical form while it reduces (no host scan of 6e9 nnz)
+            out = _device.tfidf_csr(dev, log_tf, log_idf, log_tfidf, scale_factor, inplace_values=True,
+                                    check_canonical=(attempt == 0))
+            if out is not None:
+                break
+            X = _canonical_csr(X)
         # the sparsity pattern is untouched on the device: reuse the host index arrays
         res = out.get(indptr_host=X.indptr, indices_host=X.indices)
+        if cdt == np.float32:
+            _device.remember_resident(res, out)  # lets lsi() skip the re-upload
 
     if not inplace:
         return res

@@ -42,10 +42,10 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     else:
         import scipy.sparse as sp
         Xs = X if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
-        Xs = Xs.tocsr()
-        if not Xs.has_sorted_indices:
-            Xs = Xs.sorted_indices()
-        A = _device.DeviceCSR.from_scipy(Xs, dtype=np.float32)
+        Xs = Xs.tocsr()  # row order inside a row is irrelevant to the SpMM kernels
+        A = _device.recall_resident(Xs)
+        if A is None:
+            A = _device.DeviceCSR.from_scipy(Xs, dtype=np.float32)
     n_total = A.n_total
     if n_comps >= min(n_total, A.shape[1]):  # svds' own requirement, scipy _svds.py:40-44
         raise ValueError(f"`k` must be an integer satisfying `0 < k < min(A.shape)` (k={n_comps})")

@@ -23,13 +23,15 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                     const T* __restrict__ data, int64_t n_rows, T* __restrict__ row_sum,
-                    T* __restrict__ col_sum) {
+                    T* __restrict__ col_sum, int* __restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
+    int bad = 0;  // bit0: indices not strictly increasing inside a row, bit1: explicit zero
     for (int64_t row = warp; row < n_rows; row += n_warps) {
         const int64_t start = __ldg(indptr + row), end = __ldg(indptr + row + 1);
         T acc = 0;
+        int carry = -1;  // last column index of the previous 32-wide segment of this row
         int64_t k = start + lane;
         // 4 independent coalesced segments in flight per lane
         for (; k + 96 < end; k += 128) {
@@ -42,16 +44,34 @@ tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
             atomicAdd(col_sum + c2, v2);
             atomicAdd(col_sum + c3, v3);
             acc += (v0 + v1) + (v2 + v3);
+            // canonical-form check: each index must exceed its predecessor in the row
+            int p0 = __shfl_up_sync(0xffffffffu, c0, 1), p1 = __shfl_up_sync(0xffffffffu, c1, 1);
+            int p2 = __shfl_up_sync(0xffffffffu, c2, 1), p3 = __shfl_up_sync(0xffffffffu, c3, 1);
+            const int l0 = __shfl_sync(0xffffffffu, c0, 31), l1 = __shfl_sync(0xffffffffu, c1, 31);
+            const int l2 = __shfl_sync(0xffffffffu, c2, 31), l3 = __shfl_sync(0xffffffffu, c3, 31);
+            if (lane == 0) { p0 = carry; p1 = l0; p2 = l1; p3 = l2; }
+            carry = l3;
+            bad |= (c0 <= p0) | (c1 <= p1) | (c2 <= p2) | (c3 <= p3);
+            bad |= ((v0 == T(0)) | (v1 == T(0)) | (v2 == T(0)) | (v3 == T(0))) << 1;
         }
-        for (; k < end; k += 32) {
-            int c = ld_stream(indices + k);
-            T v = ld_stream(data + k);
-            atomicAdd(col_sum + c, v);
-            acc += v;
+        for (; k - lane < end; k += 32) {  // warp-uniform trip count (shuffles inside)
+            const bool ok = k < end;
+            int c = ok ? ld_stream(indices + k) : 0x7fffffff;
+            T v = ok ? ld_stream(data + k) : T(1);
+            if (ok) {
+                atomicAdd(col_sum + c, v);
+                acc += v;
+            }
+            int p = __shfl_up_sync(0xffffffffu, c, 1);
+            const int last = __shfl_sync(0xffffffffu, c, 31);
+            if (lane == 0) p = carry;
+            carry = last;
+            bad |= (ok && c <= p) | ((ok && v == T(0)) << 1);
         }
         acc = warp_sum(acc);
         if (lane == 0) row_sum[row] = acc;
     }
+    if (status != nullptr && bad) atomicOr(status, bad);
 }
 
 template <typename T>
@@ -127,12 +147,12 @@ static int grid_for_rows(int64_t n_rows) {
 
 template <typename T>
 int tfidf_reduce(const int64_t* indptr, const int32_t* indices, const T* data, int64_t n_rows,
-                 int32_t n_cols, T* row_sum, T* col_sum, mub_stream_t stream) {
+                 int32_t n_cols, T* row_sum, T* col_sum, int* status, mub_stream_t stream) {
     MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_reduce: negative shape");
     if (n_rows == 0) return 0;
     MUB_REQUIRE(indptr && row_sum && col_sum, "tfidf_reduce: null pointer");
     tfidf_reduce_kernel<T><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
-        indptr, indices, data, n_rows, row_sum, col_sum);
+        indptr, indices, data, n_rows, row_sum, col_sum, status);
     return check_launch("tfidf_reduce");
 }
 
@@ -163,12 +183,14 @@ int tfidf_apply(const int64_t* indptr, const int32_t* indices, const T* data_in,
 extern "C" {
 
 int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
-                         int32_t n_cols, float* row_sum, float* col_sum, mub_stream_t stream) {
-    return mub::tfidf_reduce<float>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, stream);
+                         int32_t n_cols, float* row_sum, float* col_sum, int32_t* status,
+                         mub_stream_t stream) {
+    return mub::tfidf_reduce<float>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, stream);
 }
 int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const double* data, int64_t n_rows,
-                         int32_t n_cols, double* row_sum, double* col_sum, mub_stream_t stream) {
-    return mub::tfidf_reduce<double>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, stream);
+                         int32_t n_cols, double* row_sum, double* col_sum, int32_t* status,
+                         mub_stream_t stream) {
+    return mub::tfidf_reduce<double>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, stream);
 }
 int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags, float* idf,
                       mub_stream_t stream) {
