@@ -96,6 +96,11 @@ int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const 
                            const int64_t* t_indptr, int64_t* cursor, int32_t* t_indices,
                            float* t_data, mub_stream_t stream);
 
+/* per-row sum and sum of squares of a CSR (fp64).  On the CSR of A^T these are the per-feature
+ * moments behind MOFA's centring / intercepts (muon/_core/tools.py:283-287, mofapy2 process_data). */
+int mub_csr_row_stats_f32(const int64_t* indptr, const float* data, int64_t n_rows, double* sum,
+                          double* sumsq, mub_stream_t stream);
+
 /* ---- tall-skinny Gram (the k x k contraction that is allreduced across cell shards) ------
  * G[l x l] = Y^T Y for Y[n x ld] row-major, float64 result (partials are fp32 per CTA slab,
  * combined in fp64 in a fixed order: deterministic).  Replaces the dense Gram inside
@@ -104,6 +109,28 @@ int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const 
 size_t mub_gram_workspace_bytes(int64_t n, int32_t ld);
 int mub_gram_f32(const float* Y, const float* weights, int64_t n, int32_t ld, int32_t l, double* G,
                  void* workspace, mub_stream_t stream);
+
+/* ---- MOFA+ variational updates (mofapy2 training loop reached from muon/_core/tools.py:583-585;
+ * equations restated in oracle/mofa_ref.py).  One thread per row, Gauss-Seidel over the K factors,
+ * fp64 arithmetic on fp32 storage.  Dense operands are row-major with leading dimension ld >= K.
+ * Centring is implicit: Praw = Y^T E[Z] of the UN-centred sparse view, mu[D] the feature means
+ * (NULL = no centring), zsum[K] = column sums of E[Z]; inv_scale = 1/std for scale_views.
+ *   update_w : spike-and-slab weights of one view; ZZ[KxK] = E[Z^T Z] (E[z^2] on the diagonal);
+ *              tau[D] = E[tau]; alpha/lnth/ln1mth[K] = E[alpha], E[ln theta], E[ln(1-theta)].
+ *              W is read (current means) and overwritten; WW = E[(sw)^2], S = q(s=1),
+ *              What2 = E[what^2] (both branches) are written.
+ *   update_z : factors; Q = sum_m Y_m (tau*W_m) un-centred, qshift[K] its centring correction,
+ *              GW[KxK] = sum_m W^T diag(tau) W, zvar[K] = Var[z_k].  Z read and overwritten.
+ *   tau      : b_out[D] = b0 + 1/2 E||y_d - Z w_d||^2 from ssq[D] (centred sum of squares). */
+int mub_mofa_update_w_f32(const float* Praw, const float* mu, const double* zsum, double inv_scale,
+                          const double* ZZ, const float* tau, const double* alpha, const double* lnth,
+                          const double* ln1mth, float* W, float* WW, float* S, float* What2, int64_t D,
+                          int32_t ld, int32_t K, int32_t spikeslab, mub_stream_t stream);
+int mub_mofa_update_z_f32(const float* Q, const double* qshift, const double* GW, const double* zvar, float* Z,
+                          int64_t N, int32_t ld, int32_t K, mub_stream_t stream);
+int mub_mofa_tau_f32(const float* Praw, const float* mu, const double* zsum, double inv_scale, const double* ZZ,
+                     const double* ssq, const float* W, const float* WW, double b0, double* b_out, int64_t D,
+                     int32_t ld, int32_t K, mub_stream_t stream);
 
 /* ---- synthetic ATAC count generator (benchmark / test input) ---------------
  * Deterministic counter-based planted-topic model; bit-identical to the numpy generator in

@@ -1,0 +1,265 @@
+"""TEST INFRASTRUCTURE ONLY (CPU oracle) -- MOFA+ variational inference restated in numpy float64.
+
+``muon.tl.mofa`` (reference muon/_core/tools.py:290-708) densifies every modality
+(tools.py:117-141), hands the arrays to the third-party **mofapy2** package
+(``entry_point.build()/run()``, tools.py:583-585) and reads E[Z], E[W] and the variance
+explained back (tools.py:604-701).  mofapy2 is NOT vendored in the reference, NOT pinned by it
+(pyproject test-extra unpinned; CI installs git HEAD) and NOT installable here (no network).
+
+PARITY UNPINNED against mofapy2's numerics: this file restates the published MOFA / MOFA+
+coordinate-ascent updates (Argelaguet et al., Mol Syst Biol 2018, Appendix; Genome Biol 2020)
+in the order mofapy2 schedules them (W -> Z -> AlphaW -> AlphaZ -> ThetaW -> Tau, ELBO every
+iteration; SURVEY App. C, marked [recalled] there).  mofapy2's RNG stream cannot be reproduced,
+so the reference's two golden factor values (tests/test_muon_tools.py:139-147) are unreachable;
+what IS pinned is the reference's solver-agnostic structural test (tests/test_muon_tools.py:12-44:
+planted 5 factors, 10 fitted, per-factor R^2 > 0.1 for the first five and <= 0.1 for the rest,
+factors sorted by variance explained) -- see tests/test_oracle_mofa.py.  The CUDA path is then
+checked against THIS restatement from an identical initial state.
+
+Model (gaussian views m, one group, no missing values):
+    y_nd = sum_k z_nk w_dk + eps,  eps ~ N(0, 1/tau_d)
+    z_nk ~ N(0, 1/alphaZ_k)                      (ard_factors; fixed N(0,1) otherwise)
+    w_dk = s_dk * what_dk,  what ~ N(0, 1/alphaW_k),  s ~ Bernoulli(theta_k)   (spike-and-slab)
+    alpha, tau ~ Gamma(1e-3, 1e-3);  theta ~ Beta(1, 1)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.special import digamma, expit, gammaln
+
+A0 = B0 = 1e-3          # Gamma hyper-prior of alpha and tau
+TH_A0 = TH_B0 = 1.0     # Beta hyper-prior of theta
+TOLERANCE = {"fast": 5e-4, "medium": 5e-5, "slow": 5e-6}   # % change of the ELBO
+
+
+@dataclass
+class MofaState:
+    Z: np.ndarray                       # N x K   E[z]
+    Zvar: np.ndarray                    # K       Var[z_nk] (same for all n: no missing values)
+    W: list                             # per view D_m x K   E[s w]
+    WW: list                            # per view D_m x K   E[(s w)^2]
+    S: list                             # per view D_m x K   q(s=1)
+    What2: list                         # per view D_m x K   E[what^2] (both branches), for AlphaW
+    alphaW: list                        # per view (a[K], b[K])
+    alphaZ: tuple                       # (a[K], b[K])
+    theta: list                         # per view (a[K], b[K])
+    tau: list                           # per view (a[D], b[D])
+    elbo: list = field(default_factory=list)
+    iterations: int = 0
+    converged: bool = False
+
+
+def preprocess(views, center=True, scale_views=False):
+    """process_data of mofapy2 as reached from tools.py:283-287: per-feature centring of each view
+    (one group), optional division by the view's global standard deviation.  Returns dense
+    float64 arrays, the feature means (``intercepts``, tools.py:283-286) and the scale factors."""
+    out, means, scales = [], [], []
+    for Y in views:
+        Y = np.asarray(Y.todense() if hasattr(Y, "todense") else Y, dtype=np.float64)  # tools.py:117-141
+        mu = Y.mean(axis=0) if center else np.zeros(Y.shape[1])
+        Yc = Y - mu
+        sc = float(Yc.std()) if scale_views else 1.0
+        out.append(Yc / sc)
+        means.append(mu)
+        scales.append(sc)
+    return out, means, scales
+
+
+def init_state(N, dims, K, seed=1, Z0=None):
+    """Initial variational state.  Z ~ N(0,1) drawn from ``np.random.RandomState(seed)``
+    (mofapy2 seeds numpy and draws Z at random [recalled]); everything else at prior means."""
+    rs = np.random.RandomState(seed)
+    Z = rs.normal(size=(N, K)) if Z0 is None else np.array(Z0, dtype=np.float64)
+    st = MofaState(
+        Z=Z, Zvar=np.ones(K),
+        W=[np.zeros((D, K)) for D in dims], WW=[np.zeros((D, K)) for D in dims],
+        S=[np.ones((D, K)) for D in dims], What2=[np.ones((D, K)) for D in dims],
+        alphaW=[(np.ones(K), np.ones(K)) for _ in dims], alphaZ=(np.ones(K), np.ones(K)),
+        theta=[(np.ones(K), np.full(K, 1e-8)) for _ in dims],      # E[theta] ~ 1 before sparsity kicks in
+        tau=[(np.ones(D), np.ones(D)) for D in dims])
+    return st
+
+
+def _E_gamma(ab):
+    a, b = ab
+    return a / b, digamma(a) - np.log(b)
+
+
+def _E_beta(ab):
+    a, b = ab
+    return digamma(a) - digamma(a + b), digamma(b) - digamma(a + b)
+
+
+def update_W(P, ZZ, tau, alpha, lnth, ln1mth, W, spikeslab=True):
+    """Spike-and-slab weights of one view, Gauss-Seidel over factors.
+    P = Y^T E[Z] (D x K);  ZZ = E[Z^T Z] with E[z^2] on the diagonal (K x K)."""
+    D, K = P.shape
+    W = W.copy()
+    WW = np.empty_like(W)
+    S = np.empty_like(W)
+    What2 = np.empty_like(W)
+    for k in range(K):
+        a = tau * ZZ[k, k] + alpha[k]
+        cross = W @ ZZ[k, :] - W[:, k] * ZZ[k, k]
+        b = tau * (P[:, k] - cross)
+        m, v = b / a, 1.0 / a
+        if spikeslab:
+            logit = lnth[k] - ln1mth[k] + 0.5 * np.log(alpha[k]) - 0.5 * np.log(a) + 0.5 * b * b / a
+            s = expit(logit)
+        else:
+            s = np.ones(D)
+        S[:, k] = s
+        W[:, k] = s * m
+        WW[:, k] = s * (m * m + v)
+        What2[:, k] = s * (m * m + v) + (1.0 - s) / alpha[k]
+    return W, WW, S, What2
+
+
+def update_Z(Q, GW, cW, alphaZ, Z):
+    """Factors, Gauss-Seidel over k.  Q = sum_m Y (tau*W) (N x K);  GW = sum_m W^T diag(tau) W
+    (off-diagonal use);  cW[k] = sum_m sum_d tau_d E[w_dk^2]."""
+    N, K = Q.shape
+    Z = Z.copy()
+    var = 1.0 / (alphaZ + cW)
+    for k in range(K):
+        cross = Z @ GW[k, :] - Z[:, k] * GW[k, k]
+        Z[:, k] = var[k] * (Q[:, k] - cross)
+    return Z, var
+
+
+def tau_b(ssq, P, ZZ, W, WW):
+    """1/2 E||y_d - Z w_d||^2 per feature from sufficient statistics (no N x D pass)."""
+    off = ZZ - np.diag(np.diag(ZZ))
+    quad = np.einsum("dk,kj,dj->d", W, off, W) + WW @ np.diag(ZZ)
+    return 0.5 * (ssq - 2.0 * np.sum(W * P, axis=1) + quad)
+
+
+def _kl_gamma(ab, a0, b0):
+    a, b = ab
+    E, Eln = a / b, digamma(a) - np.log(b)
+    lp = a0 * np.log(b0) - gammaln(a0) + (a0 - 1) * Eln - b0 * E
+    lq = a * np.log(b) - gammaln(a) + (a - 1) * Eln - b * E
+    return float(np.sum(lp - lq))
+
+
+def _kl_beta(ab, a0, b0):
+    a, b = ab
+    Eln, Eln1 = _E_beta(ab)
+    lp = gammaln(a0 + b0) - gammaln(a0) - gammaln(b0) + (a0 - 1) * Eln + (b0 - 1) * Eln1
+    lq = gammaln(a + b) - gammaln(a) - gammaln(b) + (a - 1) * Eln + (b - 1) * Eln1
+    return float(np.sum(lp - lq))
+
+
+def elbo(st: MofaState, N, ard_weights=True, ard_factors=True, spikeslab=True):
+    """Evidence lower bound with the 'tau trick' (valid right after the Tau update)."""
+    total = 0.0
+    K = st.Z.shape[1]
+    for m in range(len(st.W)):
+        Etau, Elntau = _E_gamma(st.tau[m])
+        total += float(np.sum(0.5 * N * (Elntau - np.log(2 * np.pi)) - Etau * (st.tau[m][1] - B0)))
+        total += _kl_gamma(st.tau[m], A0, B0)
+        Ea, Elna = _E_gamma(st.alphaW[m]) if ard_weights else (np.ones(K), np.zeros(K))
+        S = np.clip(st.S[m], 1e-300, 1.0)
+        # E ln p(what|alpha) + entropy of q(what|s) (both branches)
+        D = S.shape[0]
+        mW2 = st.What2[m]
+        lp = -0.5 * np.log(2 * np.pi) + 0.5 * Elna[None, :] - 0.5 * Ea[None, :] * mW2
+        var1 = np.where(st.S[m] > 0, st.WW[m] / np.maximum(st.S[m], 1e-300) - (st.W[m] / np.maximum(st.S[m], 1e-300)) ** 2, 1.0)
+        var1 = np.maximum(var1, 1e-300)
+        ent = S * 0.5 * np.log(2 * np.pi * np.e * var1) + (1 - S) * 0.5 * np.log(2 * np.pi * np.e / Ea[None, :])
+        total += float(np.sum(lp + ent))
+        if spikeslab:
+            lnth, ln1mth = _E_beta(st.theta[m])
+            S1 = np.clip(1 - st.S[m], 1e-300, 1.0)
+            total += float(np.sum(st.S[m] * lnth[None, :] + (1 - st.S[m]) * ln1mth[None, :]
+                                  - st.S[m] * np.log(S) - (1 - st.S[m]) * np.log(S1)))
+            total += _kl_beta(st.theta[m], TH_A0, TH_B0)
+        if ard_weights:
+            total += _kl_gamma(st.alphaW[m], A0, B0)
+    Ea, Elna = _E_gamma(st.alphaZ) if ard_factors else (np.ones(K), np.zeros(K))
+    Ez2 = (st.Z ** 2).sum(0) + N * st.Zvar
+    total += float(np.sum(0.5 * N * Elna - 0.5 * Ea * Ez2 + 0.5 * N + 0.5 * N * np.log(st.Zvar)))
+    if ard_factors:
+        total += _kl_gamma(st.alphaZ, A0, B0)
+    return total
+
+
+def variance_explained(Yc, Z, W):
+    """R^2 per factor for one (centred) view: 1 - SS(Y - z_k w_k^T) / SS(Y), in percent."""
+    ss = float((Yc ** 2).sum())
+    K = Z.shape[1]
+    r2 = np.empty(K)
+    for k in range(K):
+        res = Yc - np.outer(Z[:, k], W[:, k])
+        r2[k] = 1.0 - float((res ** 2).sum()) / ss
+    return 100.0 * r2
+
+
+def mofa_ref(views, n_factors=10, n_iterations=1000, center=True, scale_views=False, ard_weights=True,
+             ard_factors=True, spikeslab_weights=True, convergence_mode="fast", seed=1, Z0=None,
+             sort_factors=True, check_convergence=True):
+    """Run CAVI.  ``views``: list of N x D_m arrays (dense or scipy sparse).  Returns a dict with
+    Z (N x K), W (list of D_m x K), variance (list of K-vectors, %), elbo (list), state."""
+    Ys, means, scales = preprocess(views, center, scale_views)
+    N = Ys[0].shape[0]
+    dims = [Y.shape[1] for Y in Ys]
+    K = n_factors
+    st = init_state(N, dims, K, seed, Z0)
+    ssq = [(Y ** 2).sum(0) for Y in Ys]
+    tol = TOLERANCE[convergence_mode]
+
+    def stats_Z():
+        ZZ = st.Z.T @ st.Z
+        ZZ[np.diag_indices(K)] += N * st.Zvar
+        return ZZ, [Y.T @ st.Z for Y in Ys]
+
+    ZZ, P = stats_Z()
+    for it in range(n_iterations):
+        # ---- W (per view) -------------------------------------------------------------------
+        for m in range(len(Ys)):
+            Etau, _ = _E_gamma(st.tau[m])
+            Ea = _E_gamma(st.alphaW[m])[0] if ard_weights else np.ones(K)
+            lnth, ln1mth = _E_beta(st.theta[m])
+            st.W[m], st.WW[m], st.S[m], st.What2[m] = update_W(P[m], ZZ, Etau, Ea, lnth, ln1mth, st.W[m],
+                                                               spikeslab_weights)
+        # ---- Z ------------------------------------------------------------------------------
+        Q = np.zeros((N, K))
+        GW = np.zeros((K, K))
+        cW = np.zeros(K)
+        for m in range(len(Ys)):
+            Etau, _ = _E_gamma(st.tau[m])
+            tw = st.W[m] * Etau[:, None]
+            Q += Ys[m] @ tw
+            GW += st.W[m].T @ tw
+            cW += Etau @ st.WW[m]
+        EaZ = _E_gamma(st.alphaZ)[0] if ard_factors else np.ones(K)
+        st.Z, st.Zvar = update_Z(Q, GW, cW, EaZ, st.Z)
+        ZZ, P = stats_Z()
+        # ---- AlphaW, AlphaZ, ThetaW -------------------------------------------------------------
+        for m in range(len(Ys)):
+            if ard_weights:
+                st.alphaW[m] = (np.full(K, A0 + 0.5 * dims[m]), B0 + 0.5 * st.What2[m].sum(0))
+            if spikeslab_weights:
+                s1 = st.S[m].sum(0)
+                st.theta[m] = (TH_A0 + s1, TH_B0 + dims[m] - s1)
+        if ard_factors:
+            st.alphaZ = (np.full(K, A0 + 0.5 * N), B0 + 0.5 * np.diag(ZZ))
+        # ---- Tau ------------------------------------------------------------------------------
+        for m in range(len(Ys)):
+            st.tau[m] = (np.full(dims[m], A0 + 0.5 * N), B0 + tau_b(ssq[m], P[m], ZZ, st.W[m], st.WW[m]))
+        # ---- ELBO / convergence -----------------------------------------------------------------
+        st.elbo.append(elbo(st, N, ard_weights, ard_factors, spikeslab_weights))
+        st.iterations = it + 1
+        if check_convergence and it >= 1:
+            delta = 100.0 * abs((st.elbo[-1] - st.elbo[-2]) / st.elbo[0])
+            if delta < tol:
+                st.converged = True
+                break
+    var = [variance_explained(Ys[m], st.Z, st.W[m]) for m in range(len(Ys))]
+    order = np.arange(K)
+    if sort_factors:
+        order = np.argsort(-np.sum(var, axis=0), kind="stable")
+    return {"Z": st.Z[:, order], "W": [w[:, order] for w in st.W], "variance": [v[order] for v in var],
+            "elbo": st.elbo, "order": order, "state": st, "intercepts": means, "scales": scales}

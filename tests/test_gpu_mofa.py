@@ -1,0 +1,100 @@
+"""GPU parity: mu.tl.mofa (sparse CUDA path) vs the float64 CPU restatement, same initial state."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import muon_b200 as mu
+from muon_b200._containers import SimpleAnnData, SimpleMuData
+from muon_b200._mofa import run_mofa_device
+from oracle.mofa_ref import mofa_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _planted(N, dims, K, seed, density=0.15, noise=0.3):
+    """Sparse non-negative views with K planted factors (gaussian-ish residuals, non-integer values)."""
+    rng = np.random.default_rng(seed)
+    Z = rng.normal(size=(N, K))
+    views = []
+    for D in dims:
+        W = rng.normal(size=(D, K)) * (rng.random((D, K)) < 0.4)
+        Y = Z @ W.T + noise * rng.normal(size=(N, D))
+        mask = rng.random((N, D)) < density
+        views.append(sp.csr_matrix(np.where(mask, np.abs(Y) + 0.1, 0.0).astype(np.float32)))
+    return views
+
+
+def _align(A, B):
+    """Match columns of A to B by sign (same order expected)."""
+    s = np.sign((A * B).sum(0))
+    s[s == 0] = 1
+    return A * s
+
+
+@pytest.mark.parametrize("scale_views", [False, True])
+def test_device_cavi_matches_oracle(cuda, scale_views):
+    N, dims, K, T = 1500, [400, 250], 6, 15
+    views = _planted(N, dims, 4, seed=7)
+    Z0 = np.random.RandomState(1).normal(size=(N, K))
+    ref = mofa_ref(views, n_factors=K, n_iterations=T, seed=1, Z0=Z0, scale_views=scale_views,
+                   check_convergence=False, sort_factors=False)
+    dv = [mu.DeviceCSR.from_scipy(v) for v in views]
+    got = run_mofa_device(dv, K, T, N, torch.from_numpy(Z0), scale_views=scale_views, check_convergence=False,
+                          sort_factors=False)
+    # ELBO trajectory (float64 statistics on both sides) and the fp32 factor / loading matrices
+    np.testing.assert_allclose(got["elbo"], ref["elbo"], rtol=1e-5)
+    Zg, Zr = got["Z"].cpu().numpy().astype(np.float64), ref["Z"]
+    scale = np.abs(Zr).max(0)
+    active = ref["variance"][0] + ref["variance"][1] > 1.0       # factors that explain > 1 %
+    assert active.sum() >= 3
+    assert (np.abs(Zg - Zr).max(0) / scale)[active].max() < 1e-4
+    for m in range(2):
+        Wg, Wr = got["W"][m].cpu().numpy().astype(np.float64), ref["W"][m]
+        assert (np.abs(Wg - Wr).max(0) / np.abs(Wr).max(0).clip(1e-12))[active].max() < 1e-4
+        np.testing.assert_allclose(got["variance"][m].cpu().numpy()[active], ref["variance"][m][active], rtol=1e-3)
+        np.testing.assert_allclose(got["intercepts"][m].cpu().numpy(), ref["intercepts"][m], rtol=1e-6, atol=1e-9)
+
+
+def test_reference_structural_kat_through_api(cuda):
+    # reference tests/test_muon_tools.py:12-54 (dense inputs, MuData and AnnData entry)
+    np.random.seed(1000)
+    z = np.random.normal(size=(100, 5))
+    w1, w2 = np.random.normal(size=(90, 5)), np.random.normal(size=(50, 5))
+    y1 = z @ w1.T + np.random.normal(size=(100, 90))
+    y2 = z @ w2.T + np.random.normal(size=(100, 50))
+    mdata = SimpleMuData({"y1": SimpleAnnData(y1), "y2": SimpleAnnData(y2)})
+    with pytest.warns(UserWarning):                       # default use_var="highly_variable" is absent
+        assert mu.tl.mofa(mdata, n_factors=10, quiet=True, verbose=False) is None
+    assert mdata.obsm["X_mofa"].shape == (100, 10) and mdata.varm["LFs"].shape == (140, 10)
+    y = np.concatenate([y1, y2], axis=1)
+    r2 = [1 - np.sum((y - mdata.obsm["X_mofa"][:, [i]] @ mdata.varm["LFs"][:, [i]].T) ** 2) / np.sum(y ** 2)
+          for i in range(10)]
+    assert all(v > 0.1 for v in r2[:5]) and not any(v > 0.1 for v in r2[5:])
+    assert set(mdata.uns["mofa"]["variance"]) == {"y1", "y2"}
+    assert mdata.uns["mofa"]["params"]["model"]["n_factors"] == 10
+    ad = SimpleAnnData(y1)
+    with pytest.warns(UserWarning):
+        mu.tl.mofa(ad, n_factors=10, quiet=True)
+    assert "X_mofa" in ad.obsm and "LFs" in ad.varm
+
+
+def test_api_semantics(cuda):
+    views = _planted(300, [120, 80], 3, seed=3)
+    a, b = SimpleAnnData(views[0]), SimpleAnnData(views[1])
+    a.var["highly_variable"] = np.arange(120) % 3 != 0
+    b.var["highly_variable"] = True
+    md = SimpleMuData({"rna": a, "atac": b})
+    md.var["highly_variable"] = np.concatenate([a.var["highly_variable"], b.var["highly_variable"]])
+    out = mu.tl.mofa(md, n_factors=4, n_iterations=20, copy=True)
+    assert out is not md and "X_mofa" not in md.obsm
+    lfs = out.varm["LFs"]
+    assert lfs.shape == (200, 4)
+    assert np.all(lfs[:120][np.arange(120) % 3 == 0] == 0) and np.any(lfs[:120][np.arange(120) % 3 != 0] != 0)
+    with pytest.raises(TypeError):
+        mu.tl.mofa(np.ones((3, 3)))
+    c = SimpleAnnData(views[1][:250])
+    with pytest.raises(IndexError):
+        mu.tl.mofa(SimpleMuData({"rna": a, "atac": c}), use_var=None)
+    with pytest.raises(NotImplementedError):
+        mu.tl.mofa(md, use_var=None, likelihoods="poisson")
