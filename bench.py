@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="one extra, synchronising step with phase timers")
     return ap.parse_args()
 
 
@@ -238,6 +239,16 @@ def main():
                              "frac": 20.0 * nnz / (t * 1e-3) / 1e9 / hbm}
     phase_ms = {name: float(np.sum(v)) / args.steps for name, v in kern.items()}
 
+    breakdown = None
+    if args.breakdown:
+        _lib.PHASES = {}
+        t0 = time.perf_counter()
+        with _lib.phase("total"):
+            ad, _ = step()
+        del ad
+        breakdown = {k: round(1e3 * v, 2) for k, v in _lib.PHASES.items()}
+        _lib.PHASES = None
+
     # ---- e2e: same public calls on HOST matrices -------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -293,7 +304,7 @@ def main():
                        "lsi": {"block": info.block, "iterations": info.iterations, "passes": info.passes,
                                "tol": args.tol, "converged": info.converged, "max_rel_residual": max(info.residuals)}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "phase_ms_per_step": phase_ms,
+            "phase_ms_per_step": phase_ms, "breakdown_ms": breakdown,
         }
         print(json.dumps(out))
     if world > 1:

@@ -112,3 +112,25 @@ def ptr(t):
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- optional coarse phase timing (bench.py --breakdown): synchronising, so never on by default
+import contextlib
+import time as _time
+
+PHASES = None   # None, or dict name -> seconds
+
+
+@contextlib.contextmanager
+def phase(name: str):
+    if PHASES is None:
+        yield
+        return
+    import torch
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    try:
+        yield
+    finally:
+        torch.cuda.synchronize()
+        PHASES[name] = PHASES.get(name, 0.0) + _time.perf_counter() - t0

@@ -35,6 +35,7 @@ from typing import Optional
 import torch
 
 from . import _dist
+from ._lib import phase
 
 
 @dataclass
@@ -56,7 +57,8 @@ class CsrOperator:
         from . import _device
         self._dev = _device
         self.A = A
-        self.At = A.transpose()
+        with phase("lsi.transpose"):
+            self.At = A.transpose()
         self.n_local, self.d = A.shape
         self.n_total = A.n_total
         self.device = A.data.device
@@ -64,12 +66,14 @@ class CsrOperator:
 
     def av(self, V):
         self.passes += 1
-        return self._dev.spmm(self.A, V, dynamic=False)
+        with phase("lsi.spmm_av"):
+            return self._dev.spmm(self.A, V, dynamic=False)
 
     def aty(self, Y):
         self.passes += 1
-        W = self._dev.spmm(self.At, Y, dynamic=True)
-        return _dist.all_reduce_sum_(W)
+        with phase("lsi.spmm_aty"):
+            W = self._dev.spmm(self.At, Y, dynamic=True)
+            return _dist.all_reduce_sum_(W)
 
     def gram(self, Y, l):
         return self._dev.gram(Y, l, reduce=True)
@@ -101,6 +105,7 @@ def _cholqr2(op, Y: torch.Tensor, l: int):
     """Y[n x P] (first l columns meaningful) -> Q (same layout, orthonormal over all shards), R[l x l] fp64."""
     R_tot = None
     for _ in range(2):
+      with phase("lsi.cholqr"):
         G = op.gram(Y, l)
         R = _chol_upper(G)
         Rinv = torch.linalg.solve_triangular(R, torch.eye(l, dtype=R.dtype, device=R.device), upper=True)
@@ -161,18 +166,21 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
             # ---- right side: W = A^T U_j - V_j R_j^T, full reorth, QR --------------------
             W = op.aty(U)[:, :bj].clone()
             info.passes += 1
-            W -= Vall[:, j0:j1] @ Bmat[j0:j1, j0:j1].T.to(torch.float32)
-            W, _ = _orth_against(W, Vall[:, :m])
+            with phase("lsi.reorth"):
+                W -= Vall[:, j0:j1] @ Bmat[j0:j1, j0:j1].T.to(torch.float32)
+                W, _ = _orth_against(W, Vall[:, :m])
             bn = min(bj, m_cap - m, d - m)     # width of the next block
             Sj = None
             if d - m > 0:
+              with phase("lsi.qr"):
                 Qn, S1 = torch.linalg.qr(W)
                 # rank-deficient W leaves arbitrary directions in Qn: clean them against the basis
                 Qn, _ = _orth_against(Qn.contiguous(), Vall[:, :m], passes=1)
                 Qn, S2 = torch.linalg.qr(Qn)
                 Sj = (S2.to(f64) @ S1.to(f64))          # W = Qn Sj   (bj x bj)
             # ---- Rayleigh-Ritz on the block-bidiagonal B (fp64, tiny) ---------------------
-            X, sig, Zt = torch.linalg.svd(Bmat[:m, :m])
+            with phase("lsi.ritz_svd"):
+                X, sig, Zt = torch.linalg.svd(Bmat[:m, :m])
             kk = min(k, m)
             if Sj is not None:
                 res = torch.linalg.norm(Sj @ X[j0:j1, :kk], dim=0) / sig[:kk].clamp_min(1e-300)

@@ -23,6 +23,7 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     import torch
 
     from .. import _device, _dist
+    from .._lib import phase
     from .._lsi import CsrOperator, truncated_svd
 
     if is_anndata(data):
@@ -55,6 +56,8 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     U, s, V, info = truncated_svd(op, n_comps, P, tol=tol, seed=seed)
 
     # post-processing of tools.py:60-65 on the device (moments allreduced over cell shards)
+    _ph = phase("lsi.post_and_d2h")
+    _ph.__enter__()
     emb = U
     if scale_embeddings:
         mom = torch.stack([U.sum(0, dtype=torch.float64), (U.to(torch.float64) ** 2).sum(0)])
@@ -68,6 +71,7 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     adata.obsm["X_lsi"] = emb.cpu().numpy().astype(out_dtype, copy=False)
     adata.uns["lsi"] = {"stdev": stdev.cpu().numpy().astype(out_dtype, copy=False)}
     adata.varm["LSI"] = V.cpu().numpy().astype(out_dtype, copy=False)
+    _ph.__exit__(None, None, None)
     if return_info:
         return info
     return None

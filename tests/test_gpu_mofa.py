@@ -12,16 +12,15 @@ from oracle.mofa_ref import mofa_ref
 pytestmark = pytest.mark.gpu
 
 
-def _planted(N, dims, K, seed, density=0.15, noise=0.3):
-    """Sparse non-negative views with K planted factors (gaussian-ish residuals, non-integer values)."""
+def _planted(N, dims, K, seed, noise=0.5):
+    """Sparse non-negative views (about 19 % non-zero, non-integer values) with K planted factors."""
     rng = np.random.default_rng(seed)
     Z = rng.normal(size=(N, K))
     views = []
     for D in dims:
-        W = rng.normal(size=(D, K)) * (rng.random((D, K)) < 0.4)
-        Y = Z @ W.T + noise * rng.normal(size=(N, D))
-        mask = rng.random((N, D)) < density
-        views.append(sp.csr_matrix(np.where(mask, np.abs(Y) + 0.1, 0.0).astype(np.float32)))
+        W = rng.normal(size=(D, K)) * (rng.random((D, K)) < 0.5)
+        Y = Z @ W.T + noise * rng.normal(size=(N, D)) - 1.0
+        views.append(sp.csr_matrix(np.maximum(Y, 0).astype(np.float32)))
     return views
 
 
