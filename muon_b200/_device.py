@@ -31,44 +31,70 @@ def pad_width(l: int) -> int:
 
 
 _STAGE_BYTES = 256 << 20
+_PINNED = []          # two cached pinned staging buffers (uint8), allocated on first large transfer
+_POOL = None          # thread pool for host-side memcpy into / out of the staging buffers
+_COPY_THREADS = 16
+
+
+def _staging():
+    global _POOL
+    if not _PINNED:
+        _PINNED.extend(torch.empty(_STAGE_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2))
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(_COPY_THREADS)
+    return _PINNED
+
+
+def _parallel_copy(dst: np.ndarray, src: np.ndarray):
+    """dst[:] = src for 1-D arrays of equal dtype, split over threads (numpy releases the GIL);
+    a single-threaded memcpy (and first-touch page faults) would cap PCIe staging at ~3 GB/s."""
+    n = dst.shape[0]
+    parts = max(1, min(_COPY_THREADS, (n * dst.itemsize) >> 22))
+    if parts == 1:
+        np.copyto(dst, src)
+        return
+    bounds = [n * i // parts for i in range(parts + 1)]
+    list(_POOL.map(lambda i: np.copyto(dst[bounds[i]:bounds[i + 1]], src[bounds[i]:bounds[i + 1]]), range(parts)))
 
 
 def to_device(arr, device, dtype=None) -> torch.Tensor:
     """Host array -> device tensor of numpy dtype ``dtype`` (default: unchanged).
 
-    Pinned inputs go in one async copy.  Pageable inputs are staged through two pinned buffers
-    so the PCIe copy of one chunk overlaps the host memcpy of the next; a dtype change
-    (e.g. scipy's int64 indices -> int32) happens on the device per chunk, never on the host."""
+    Pinned inputs go in one async copy.  Pageable inputs are staged through two cached pinned
+    buffers (multi-threaded host memcpy overlapping the PCIe copy of the previous chunk); a dtype
+    change (e.g. scipy's int64 indices -> int32) happens on the device per chunk, never on the host."""
     if isinstance(arr, torch.Tensor):
-        t = arr
-    else:
-        a = np.ascontiguousarray(arr)
+        if arr.device.type == "cuda":
+            tgt = arr.dtype if dtype is None else getattr(torch, np.dtype(dtype).name)
+            return arr if arr.dtype == tgt else arr.to(tgt)
+        arr = arr.numpy()
+    a = np.ascontiguousarray(arr)
+    tgt = getattr(torch, np.dtype(a.dtype if dtype is None else dtype).name)
+    nbytes = a.nbytes
+    if nbytes <= (8 << 20):
         if not a.flags.writeable:
             a = a.copy()
-        t = torch.from_numpy(a)
-    tgt = t.dtype if dtype is None else getattr(torch, np.dtype(dtype).name)
-    if t.device.type == "cuda":
-        return t if t.dtype == tgt else t.to(tgt)
-    nbytes = t.numel() * t.element_size()
-    if t.is_pinned() or nbytes <= _STAGE_BYTES:
-        out = t.to(device, non_blocking=True)
+        out = torch.from_numpy(a).to(device, non_blocking=False)
         return out if out.dtype == tgt else out.to(tgt)
-    out = torch.empty(t.shape, dtype=tgt, device=device)
-    flat_src, flat_dst = t.reshape(-1), out.reshape(-1)
-    step = _STAGE_BYTES // t.element_size()
-    stage = [torch.empty(step, dtype=t.dtype).pin_memory() for _ in range(2)]
-    dstage = [torch.empty(step, dtype=t.dtype, device=device) for _ in range(2)] if tgt != t.dtype else None
+    src_t = getattr(torch, a.dtype.name)
+    flat = a.reshape(-1)
+    out = torch.empty(a.shape, dtype=tgt, device=device)
+    flat_dst = out.reshape(-1)
+    stage = _staging()
+    step = _STAGE_BYTES // a.itemsize
+    dstage = [torch.empty(step, dtype=src_t, device=device) for _ in range(2)] if tgt != src_t else None
     events = [None, None]
-    for i, off in enumerate(range(0, flat_src.numel(), step)):
-        s = stage[i & 1]
+    for i, off in enumerate(range(0, flat.shape[0], step)):
+        n = min(step, flat.shape[0] - off)
+        s = stage[i & 1][: n * a.itemsize].view(src_t)
         if events[i & 1] is not None:
             events[i & 1].synchronize()
-        n = min(step, flat_src.numel() - off)
-        s[:n].copy_(flat_src[off:off + n])
+        _parallel_copy(s.numpy(), flat[off:off + n])
         if dstage is None:
-            flat_dst[off:off + n].copy_(s[:n], non_blocking=True)
+            flat_dst[off:off + n].copy_(s, non_blocking=True)
         else:
-            dstage[i & 1][:n].copy_(s[:n], non_blocking=True)
+            dstage[i & 1][:n].copy_(s, non_blocking=True)
             flat_dst[off:off + n].copy_(dstage[i & 1][:n])
         ev = torch.cuda.Event()
         ev.record()
@@ -78,24 +104,24 @@ def to_device(arr, device, dtype=None) -> torch.Tensor:
 
 
 def to_host(t: torch.Tensor, out: Optional[np.ndarray] = None) -> np.ndarray:
-    """Device tensor -> numpy array, staged through pinned buffers for large transfers."""
-    nbytes = t.numel() * t.element_size()
+    """Device tensor -> numpy array, staged through the pinned buffers for large transfers."""
+    np_dt = np.dtype(str(t.dtype).split(".")[1])
     if out is None:
-        out = np.empty(tuple(t.shape), dtype=getattr(np, str(t.dtype).split(".")[1]))
-    dst = torch.from_numpy(out).reshape(-1)
+        out = np.empty(tuple(t.shape), dtype=np_dt)
+    nbytes = t.numel() * t.element_size()
     src = t.reshape(-1)
-    if nbytes <= _STAGE_BYTES or dst.is_pinned():
-        dst.copy_(src)
+    dst = out.reshape(-1)
+    if nbytes <= (8 << 20):
+        torch.from_numpy(dst).copy_(src)
         return out
+    stage = _staging()
     step = _STAGE_BYTES // t.element_size()
-    stage = [torch.empty(step, dtype=t.dtype).pin_memory() for _ in range(2)]
-    events = [None, None]
-    pending = [None, None]
-    chunks = list(range(0, src.numel(), step))
-    for i, off in enumerate(chunks + [None]):
+    events, pending = [None, None], [None, None]
+    offs = list(range(0, src.numel(), step))
+    for i, off in enumerate(offs + [None]):
         if off is not None:
             n = min(step, src.numel() - off)
-            stage[i & 1][:n].copy_(src[off:off + n], non_blocking=True)
+            stage[i & 1][: n * t.element_size()].view(t.dtype).copy_(src[off:off + n], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             events[i & 1], pending[i & 1] = ev, (off, n)
@@ -103,7 +129,7 @@ def to_host(t: torch.Tensor, out: Optional[np.ndarray] = None) -> np.ndarray:
         if i >= 1 and pending[j] is not None:
             events[j].synchronize()
             o, n = pending[j]
-            dst[o:o + n].copy_(stage[j][:n])
+            _parallel_copy(dst[o:o + n], stage[j][: n * t.element_size()].view(t.dtype).numpy())
             pending[j] = None
     return out
 
@@ -190,6 +216,12 @@ class DeviceCSR:
             self._t = csr_transpose(self)
         return self._t
 
+    def transpose_panels(self, pad: int = 64) -> "TransposedPanels":
+        key = ("panels", pad)
+        if getattr(self, "_tp", None) is None or self._tp[0] != key:
+            self._tp = (key, TransposedPanels(self, pad))
+        return self._tp[1]
+
 
 # ------------------------------------------------------------------------------------------
 def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=1e4,
@@ -223,22 +255,57 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
     return res
 
 
-def csr_transpose(A: DeviceCSR) -> DeviceCSR:
-    """Build the CSR of A^T on the device (count -> scan -> atomic-cursor fill)."""
+def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None) -> DeviceCSR:
+    """Build the CSR of (A[row0:row1])^T on the device (count -> scan -> atomic-cursor fill).
+    Row indices stored in the result are local to the panel (0 .. row1-row0)."""
     require_cuda()
     assert A.data.dtype == torch.float32, "transpose: float32 values only"
     n, d = A.shape
+    row1 = n if row1 is None else row1
     dev = A.data.device
     st = stream_ptr()
+    if row0 == 0 and row1 == n:
+        k0, k1 = 0, A.nnz
+    else:
+        k0, k1 = int(A.indptr[row0]), int(A.indptr[row1])
+    nnz = k1 - k0
     t_count = torch.zeros(d + 1, dtype=torch.int64, device=dev)
-    call("mub_csr_transpose_count", ptr(A.indices), A.nnz, d, ptr(t_count), st)
+    call("mub_csr_transpose_count", ptr(A.indices) + 4 * k0, nnz, d, ptr(t_count), st)
     t_indptr = torch.cumsum(t_count, 0)
     cursor = torch.empty(max(d, 1), dtype=torch.int64, device=dev)
-    t_indices = torch.empty(A.nnz, dtype=torch.int32, device=dev)
-    t_data = torch.empty(A.nnz, dtype=torch.float32, device=dev)
-    call("mub_csr_transpose_fill", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, 0, ptr(t_indptr), ptr(cursor),
-         ptr(t_indices), ptr(t_data), st)
-    return DeviceCSR(t_indptr, t_indices, t_data, (d, n), n_total=d, sorted_indices=False)
+    t_indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    t_data = torch.empty(nnz, dtype=torch.float32, device=dev)
+    # indptr values are absolute offsets into indices/data, so only the indptr pointer is shifted;
+    # slots claimed from `cursor` are panel-local, so the outputs are not
+    call("mub_csr_transpose_fill", ptr(A.indptr) + 8 * row0, ptr(A.indices), ptr(A.data), row1 - row0, d, 0,
+         ptr(t_indptr), ptr(cursor), ptr(t_indices), ptr(t_data), st)
+    return DeviceCSR(t_indptr, t_indices, t_data, (d, row1 - row0), n_total=d, sorted_indices=False)
+
+
+class TransposedPanels:
+    """A^T as a list of row-panel transposes.  A^T Y gathers rows of Y (n x P); when n*P*4 bytes
+    exceed what stays resident in L2 the gathers fall through to HBM, so the cells are cut into
+    panels whose slice of Y fits in L2 and the products are accumulated panel by panel."""
+
+    L2_BUDGET = 64 << 20   # bytes of the gathered operand per panel (B200 L2: 126 MB)
+
+    def __init__(self, A: DeviceCSR, pad: int = 64):
+        n = A.shape[0]
+        rows = max(1, self.L2_BUDGET // (4 * pad))
+        n_panels = max(1, -(-n // rows))
+        bounds = [round(i * n / n_panels) for i in range(n_panels + 1)]
+        self.shape = (A.shape[1], n)
+        self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1]))
+                       for i in range(n_panels)]
+
+    def spmm(self, Y: torch.Tensor, dynamic=True) -> torch.Tensor:
+        out = None
+        for r0, r1, T in self.panels:
+            if out is None:
+                out = spmm(T, Y[r0:r1], dynamic=dynamic)
+            else:
+                spmm(T, Y[r0:r1], out=out, accumulate=True, dynamic=dynamic)
+        return out
 
 
 def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False,

@@ -53,12 +53,12 @@ class SvdInfo:
 class CsrOperator:
     """A (cell shard) and A^T as CUDA SpMM + Gram kernels."""
 
-    def __init__(self, A):
+    def __init__(self, A, pad: int = 64):
         from . import _device
         self._dev = _device
         self.A = A
         with phase("lsi.transpose"):
-            self.At = A.transpose()
+            self.At = A.transpose_panels(pad)
         self.n_local, self.d = A.shape
         self.n_total = A.n_total
         self.device = A.data.device
@@ -72,7 +72,7 @@ class CsrOperator:
     def aty(self, Y):
         self.passes += 1
         with phase("lsi.spmm_aty"):
-            W = self._dev.spmm(self.At, Y, dynamic=True)
+            W = self.At.spmm(Y, dynamic=True)
             return _dist.all_reduce_sum_(W)
 
     def gram(self, Y, l):
@@ -143,9 +143,10 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
     info = SvdInfo(block=b)
     f64 = torch.float64
 
-    g = torch.Generator(device="cpu").manual_seed(int(seed))
-    V0 = torch.randn((d, b), generator=g, dtype=torch.float32).to(dev)
-    V0, _ = torch.linalg.qr(V0)
+    with phase("lsi.init"):
+        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        V0 = torch.randn((d, b), generator=g, dtype=torch.float32).to(dev)
+        V0, _ = torch.linalg.qr(V0)
 
     Vk = None
     for restart in range(max_restarts + 1):
@@ -199,17 +200,19 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
             if rmax <= tol or stagn >= 2 or bn <= 0:
                 done = (rmax <= tol) or stagn >= 2 or m >= d
                 info.residuals = res.tolist()
-                Vk = Vall[:, :m] @ Zt[:kk, :].T.to(torch.float32)      # d x k right Ritz vectors
-                V0_next = Vall[:, :m] @ Zt[:b, :].T.to(torch.float32)
+                with phase("lsi.ritz_vectors"):
+                    Vk = Vall[:, :m] @ Zt[:kk, :].T.to(torch.float32)      # d x k right Ritz vectors
+                    V0_next = Vall[:, :m] @ Zt[:b, :].T.to(torch.float32)
                 break
             # ---- left side: Y = A V_{j+1} - U_j S_j^T, CholeskyQR2 --------------------------
             Sj_use = Sj[:bn, :]                                    # if the block shrank keep bn rows
             Vall[:, m:m + bn] = Qn[:, :bn]
             Y = op.av(_pad(Vall[:, m:m + bn], P))
             info.passes += 1
-            M = torch.zeros((P, P), dtype=torch.float32, device=dev)
-            M[:bj, :bn] = Sj_use.T.to(torch.float32)
-            Y -= U @ M
+            with phase("lsi.left_update"):
+                M = torch.zeros((P, P), dtype=torch.float32, device=dev)
+                M[:bj, :bn] = Sj_use.T.to(torch.float32)
+                Y -= U @ M
             U, Rn = _cholqr2(op, Y, bn)
             Bmat[j0:j1, m:m + bn] = Sj_use.T
             Bmat[m:m + bn, m:m + bn] = Rn
@@ -223,6 +226,8 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
         V0, _ = torch.linalg.qr(V0_next)
 
     # ---- final Rayleigh-Ritz polish, as scipy does after ARPACK (_svds.py:508-533) -------------
+    _ph = phase("lsi.final")
+    _ph.__enter__()
     Vk, _ = torch.linalg.qr(Vk)
     kk = Vk.shape[1]
     Y = op.av(_pad(Vk, P))
@@ -236,4 +241,5 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
     Mz[:kk, :] = Zs
     Uk = Y @ Mz
     Vk = Vk @ Z.to(torch.float32)
+    _ph.__exit__(None, None, None)
     return Uk, s, Vk, info

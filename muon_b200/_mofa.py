@@ -41,12 +41,17 @@ class _View:
 
     def __init__(self, A: _device.DeviceCSR, K: int, ld: int, n_total: int, center: bool, scale: bool):
         dev = A.data.device
-        self.A, self.At = A, A.transpose()
+        self.A, self.At = A, A.transpose_panels(ld)
         self.D = A.shape[1]
         D = self.D
         s1 = torch.empty(D, dtype=f64, device=dev)
         s2 = torch.empty(D, dtype=f64, device=dev)
-        call("mub_csr_row_stats_f32", ptr(self.At.indptr), ptr(self.At.data), D, ptr(s1), ptr(s2), stream_ptr())
+        for i, (_, _, T) in enumerate(self.At.panels):
+            t1, t2 = (s1, s2) if i == 0 else (torch.empty_like(s1), torch.empty_like(s2))
+            call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
+            if i:
+                s1 += t1
+                s2 += t2
         _dist.all_reduce_sum_(s1)
         _dist.all_reduce_sum_(s2)
         self.mean = s1 / n_total                                   # intercepts, tools.py:283-286
@@ -131,7 +136,7 @@ class MofaDevice:
         self.ZZ = ZZ.contiguous()
         self.zsum = _dist.all_reduce_sum_(self.Z[:, :K].sum(0, dtype=f64)).contiguous()
         for v in self.views:
-            v.P = _dist.all_reduce_sum_(_device.spmm(v.At, self.Z, dynamic=True))
+            v.P = _dist.all_reduce_sum_(v.At.spmm(self.Z, dynamic=True))
 
     def step(self):
         K, ld, st = self.K, self.ld, stream_ptr()

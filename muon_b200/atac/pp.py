@@ -68,7 +68,9 @@ def tfidf(
         warn(f"Existing layer '{str(to_layer)}' will be overwritten")
 
     if isinstance(counts, _device.DeviceCSR):
-        res = _device.tfidf_csr(counts, log_tf, log_idf, log_tfidf, scale_factor)
+        from .._lib import phase
+        with phase("tfidf"):
+            res = _device.tfidf_csr(counts, log_tf, log_idf, log_tfidf, scale_factor)
     else:
         import scipy.sparse as sp
         X = counts if sp.isspmatrix_csr(counts) else sp.csr_matrix(counts)

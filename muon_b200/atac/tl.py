@@ -51,8 +51,8 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     if n_comps >= min(n_total, A.shape[1]):  # svds' own requirement, scipy _svds.py:40-44
         raise ValueError(f"`k` must be an integer satisfying `0 < k < min(A.shape)` (k={n_comps})")
 
-    op = CsrOperator(A)
     P = _device.pad_width(min(n_comps + 8, 128) if n_comps + 8 <= 128 else n_comps)
+    op = CsrOperator(A, P)
     U, s, V, info = truncated_svd(op, n_comps, P, tol=tol, seed=seed)
 
     # post-processing of tools.py:60-65 on the device (moments allreduced over cell shards)

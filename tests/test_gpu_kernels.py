@@ -101,3 +101,16 @@ def test_generator_device_equals_host(cuda):
     np.testing.assert_array_equal(D.indptr, H.indptr)
     np.testing.assert_array_equal(D.indices, H.indices)
     np.testing.assert_array_equal(D.data, H.data)
+
+
+def test_transposed_panels_equal_full_transpose(cuda, monkeypatch):
+    X = _rand_csr(3000, 900, 0.03, 9, skew=True)
+    A = mu.DeviceCSR.from_scipy(X)
+    monkeypatch.setattr(_device.TransposedPanels, "L2_BUDGET", 700 * 64 * 4)     # force 5 panels
+    Tp = _device.TransposedPanels(A, 64)
+    assert len(Tp.panels) >= 4 and Tp.panels[0][0] == 0 and Tp.panels[-1][1] == X.shape[0]
+    Y = torch.randn((X.shape[0], 64), device=cuda)
+    Z = Tp.spmm(Y)
+    ref = X.T.astype(np.float64) @ Y.cpu().numpy().astype(np.float64)
+    scale = np.abs(X.T).astype(np.float64) @ np.abs(Y.cpu().numpy()).astype(np.float64) + 1e-30
+    assert (np.abs(Z.cpu().numpy() - ref) / scale).max() < 5e-6
