@@ -82,6 +82,14 @@ int mub_spmm_csr_f32(const int64_t* indptr, const int32_t* indices, const float*
                      int64_t n_rows, int64_t n_cols, const float* B, int32_t ld, float* C,
                      int32_t accumulate, unsigned long long* row_counter, mub_stream_t stream);
 
+/* Same product, shared-memory staged variant for matrices whose column indices are SORTED within
+ * each row (canonical CSR): column panels of B are TMA-copied (cp.async.bulk) into shared memory
+ * behind mbarriers and a persistent CTA sweeps a block of rows over them with register-resident
+ * accumulators, cutting the L2->SM gather traffic of the row-warp kernel.  Deterministic. */
+int mub_spmm_csr_panel_f32(const int64_t* indptr, const int32_t* indices, const float* data,
+                           int64_t n_rows, int64_t n_cols, const float* B, int32_t ld, float* C,
+                           int32_t accumulate, mub_stream_t stream);
+
 /* ---- CSR transpose (one-time per matrix): builds the CSR of A^T so that A^T * Y is again a
  * row-gather SpMM (scipy does the same implicitly through csc_matvec, _svds.py:447).
  * Step 1 counts entries per column into t_count[n_cols+1] (int64, zeroed by caller, slot 0 unused

@@ -5,6 +5,7 @@ the hot path is a call into ``libmuon_b200.so``.  Nothing here has a CPU fallbac
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -309,14 +310,27 @@ class TransposedPanels:
 
 
 def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False,
-         dynamic=True) -> torch.Tensor:
-    """K2/K3: C[n x P] (+)= A @ B[d x P];  P = B.shape[1] must be 32, 64 or 128."""
+         dynamic=True, algo: Optional[str] = None) -> torch.Tensor:
+    """K2/K3: C[n x P] (+)= A @ B[d x P];  P = B.shape[1] must be 32, 64 or 128.
+
+    algo: "rowwarp" (v1: warp per row, B gathered from L2), "panel" (v2: B column panels staged in
+    shared memory by TMA; needs sorted column indices) or None = $MUON_B200_SPMM or auto."""
     n, d = A.shape
     P = B.shape[1]
     assert B.shape[0] == d and B.dtype == torch.float32 and B.is_contiguous(), (B.shape, d, B.dtype)
     if out is None:
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=B.device)
+    if algo is None:
+        algo = os.environ.get("MUON_B200_SPMM", "auto")
+    if algo == "auto":
+        algo = "panel" if (A.sorted_indices and d >= 2048 and A.nnz >= 8 * n) else "rowwarp"
+    if algo == "panel":
+        if not A.sorted_indices:
+            raise MuonB200Error("spmm(algo='panel') needs sorted column indices")
+        call("mub_spmm_csr_panel_f32", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(B), P, ptr(out),
+             1 if accumulate else 0, stream_ptr())
+        return out
     counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
     call("mub_spmm_csr_f32", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(B), P, ptr(out),
          1 if accumulate else 0, ptr(counter), stream_ptr())

@@ -114,3 +114,24 @@ def test_transposed_panels_equal_full_transpose(cuda, monkeypatch):
     ref = X.T.astype(np.float64) @ Y.cpu().numpy().astype(np.float64)
     scale = np.abs(X.T).astype(np.float64) @ np.abs(Y.cpu().numpy()).astype(np.float64) + 1e-30
     assert (np.abs(Z.cpu().numpy() - ref) / scale).max() < 5e-6
+
+
+@pytest.mark.parametrize("P", [32, 64, 128])
+def test_spmm_panel_vs_scipy(cuda, P):
+    """v2 (TMA-staged column panels): needs sorted indices; rows longer than a panel, empty rows,
+    more than one row block and more than two panels are all exercised."""
+    X = _rand_csr(1500, 5000, 0.02, 4, skew=True)
+    B = np.random.default_rng(2).standard_normal((5000, P)).astype(np.float32)
+    A = mu.DeviceCSR.from_scipy(X)
+    Bd = torch.from_numpy(B).to(cuda)
+    C = _device.spmm(A, Bd, algo="panel")
+    ref = X.astype(np.float64) @ B.astype(np.float64)
+    scale = np.abs(X).astype(np.float64) @ np.abs(B).astype(np.float64) + 1e-30
+    assert (np.abs(C.cpu().numpy() - ref) / scale).max() < 5e-6
+    C1 = _device.spmm(A, Bd, algo="rowwarp")
+    assert float((C - C1).abs().max() / C1.abs().max()) < 1e-5
+    C2 = _device.spmm(A, Bd, out=C.clone(), accumulate=True, algo="panel")
+    np.testing.assert_allclose(C2.cpu().numpy(), 2 * C.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(_device.spmm(A, Bd, algo="panel").cpu().numpy(), C.cpu().numpy())  # deterministic
+    with pytest.raises(Exception):
+        _device.spmm(A.transpose(), torch.zeros((1513, P), device=cuda), algo="panel")
