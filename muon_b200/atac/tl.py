@@ -68,9 +68,9 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     stdev = s / np.sqrt(n_total - 1)
 
     out_dtype = np.float32 if resident or X.dtype == np.float32 else np.float64
-    adata.obsm["X_lsi"] = emb.cpu().numpy().astype(out_dtype, copy=False)
+    adata.obsm["X_lsi"] = _device.to_host(emb.contiguous()).astype(out_dtype, copy=False)
     adata.uns["lsi"] = {"stdev": stdev.cpu().numpy().astype(out_dtype, copy=False)}
-    adata.varm["LSI"] = V.cpu().numpy().astype(out_dtype, copy=False)
+    adata.varm["LSI"] = _device.to_host(V.contiguous()).astype(out_dtype, copy=False)
     _ph.__exit__(None, None, None)
     if return_info:
         return info

@@ -158,10 +158,36 @@ spmm_csr_panel_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
                 for (;;) {
                     const unsigned m = __ballot_sync(0xffffffffu, c < j1);
                     const int cnt = __popc(m);  // sorted row: in-panel entries are a prefix
-                    for (int t = 0; t < cnt; ++t) {
-                        const int cc = __shfl_sync(0xffffffffu, c, t);
-                        const float vv = __shfl_sync(0xffffffffu, v, t);
-                        fma_row<VEC>(acc[r], vv, panel + (size_t)cc * P);
+                    // batches of 4 non-zeros: shuffles and shared-memory loads of a batch are issued
+                    // back to back (ILP), then the FMAs; the last batch is padded with zero weights
+                    for (int t = 0; t < cnt; t += 4) {
+                        int cc[4];
+                        float vv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int src = t + u;
+                            cc[u] = __shfl_sync(0xffffffffu, c, src & 31);
+                            vv[u] = __shfl_sync(0xffffffffu, v, src & 31);
+                            if (src >= cnt) { cc[u] = j0; vv[u] = 0.f; }
+                        }
+                        float bb[4][VEC];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float* br = panel + (size_t)cc[u] * P;
+                            if constexpr (VEC == 1) {
+                                bb[u][0] = br[0];
+                            } else if constexpr (VEC == 2) {
+                                const float2 q = *reinterpret_cast<const float2*>(br);
+                                bb[u][0] = q.x; bb[u][1] = q.y;
+                            } else {
+                                const float4 q = *reinterpret_cast<const float4*>(br);
+                                bb[u][0] = q.x; bb[u][1] = q.y; bb[u][2] = q.z; bb[u][3] = q.w;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) acc[r][e] = fmaf(vv[u], bb[u][e], acc[r][e]);
                     }
                     base += cnt;
                     if (cnt < 32) break;

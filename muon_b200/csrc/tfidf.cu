@@ -32,9 +32,11 @@ tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
         const int64_t start = __ldg(indptr + row), end = __ldg(indptr + row + 1);
         T acc = 0;
         int carry = -1;  // last column index of the previous 32-wide segment of this row
-        int64_t k = start + lane;
-        // 4 independent coalesced segments in flight per lane
-        for (; k + 96 < end; k += 128) {
+        // 4 independent coalesced segments in flight per lane; trip counts are warp-uniform
+        // (the canonical-form check below shuffles across the whole warp)
+        int64_t kb = start;
+        for (; kb + 128 <= end; kb += 128) {
+            const int64_t k = kb + lane;
             int c0 = ld_stream(indices + k), c1 = ld_stream(indices + k + 32);
             int c2 = ld_stream(indices + k + 64), c3 = ld_stream(indices + k + 96);
             T v0 = ld_stream(data + k), v1 = ld_stream(data + k + 32);
@@ -54,7 +56,8 @@ tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
             bad |= (c0 <= p0) | (c1 <= p1) | (c2 <= p2) | (c3 <= p3);
             bad |= ((v0 == T(0)) | (v1 == T(0)) | (v2 == T(0)) | (v3 == T(0))) << 1;
         }
-        for (; k - lane < end; k += 32) {  // warp-uniform trip count (shuffles inside)
+        for (; kb < end; kb += 32) {
+            const int64_t k = kb + lane;
             const bool ok = k < end;
             int c = ok ? ld_stream(indices + k) : 0x7fffffff;
             T v = ok ? ld_stream(data + k) : T(1);

@@ -16,15 +16,16 @@ A = generate_device(n, d, 0.03, tables=make_tables(d, 0.03, 64, 1))
 B = torch.randn((d, P), device="cuda")
 ref = None
 for algo in ("rowwarp", "panel"):
-    C = _device.spmm(A, B, algo=algo, dynamic=False)
+    for _ in range(10):   # warm up clocks and caches
+        C = _device.spmm(A, B, algo=algo, dynamic=False)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
-    for _ in range(5):
+    for _ in range(10):
         C = _device.spmm(A, B, algo=algo, dynamic=False)
     ev[1].record()
     torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1]) / 5
+    ms = ev[0].elapsed_time(ev[1]) / 10
     gb = (8 * A.nnz + 4 * P * (n + d)) / 1e9
     err = 0.0 if ref is None else float((C - ref).abs().max() / ref.abs().max())
     ref = C if ref is None else ref

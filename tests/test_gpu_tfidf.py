@@ -148,3 +148,29 @@ def test_device_resident_and_properties(cuda):
     X2 = sp.vstack([X, X]).tocsr()
     out2 = mu.atac.pp.tfidf(SimpleAnnData(X2), inplace=False)
     np.testing.assert_allclose(out2[:4000].data, out.data, rtol=1e-6)
+
+
+def test_canonical_input_never_takes_the_host_fallback(cuda, monkeypatch):
+    """The device-side canonical-form check must not flag canonical input (rows of every length
+    class around the 32/128-wide segment boundaries); non-canonical input must be flagged."""
+    from muon_b200.atac import pp
+    calls = []
+    orig = pp._canonical_csr
+    monkeypatch.setattr(pp, "_canonical_csr", lambda X: (calls.append(1), orig(X))[1])
+    rng = np.random.default_rng(0)
+    rows = []
+    d = 1000
+    for L in list(range(0, 140)) + [255, 256, 257, 511, 640, 999]:
+        cols = np.sort(rng.choice(d, L, replace=False))
+        rows.append(sp.csr_matrix((rng.integers(1, 4, L).astype(np.float32), (np.zeros(L, int), cols)), shape=(1, d)))
+    X = sp.vstack(rows).tocsr()
+    X.sort_indices()
+    got = mu.atac.pp.tfidf(SimpleAnnData(X.copy()), inplace=False)
+    assert not calls
+    _assert_parity(got, tfidf_ref(X), RTOL32)
+    Xu = X.copy()
+    Xu.indices[X.indptr[130]:X.indptr[130] + 2] = Xu.indices[X.indptr[130]:X.indptr[130] + 2][::-1].copy()
+    Xu.has_sorted_indices = False
+    got = mu.atac.pp.tfidf(SimpleAnnData(Xu), inplace=False)
+    assert calls
+    _assert_parity(got, tfidf_ref(X), RTOL32)
