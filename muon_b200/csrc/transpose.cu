@@ -46,7 +46,21 @@ transpose_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
     for (int64_t row = warp; row < n_rows; row += n_warps) {
         const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
         const int32_t r = (int32_t)(row + row_offset);
-        for (int64_t k = s + lane; k < e; k += 32) {
+        int64_t k = s + lane;
+        // 4 independent slot claims in flight per lane (the atomic's return latency dominates)
+        for (; k + 96 < e; k += 128) {
+            const int c0 = ld_stream(indices + k), c1 = ld_stream(indices + k + 32);
+            const int c2 = ld_stream(indices + k + 64), c3 = ld_stream(indices + k + 96);
+            const float v0 = ld_stream(data + k), v1 = ld_stream(data + k + 32);
+            const float v2 = ld_stream(data + k + 64), v3 = ld_stream(data + k + 96);
+            const unsigned long long s0 = atomicAdd(cursor + c0, 1ull), s1 = atomicAdd(cursor + c1, 1ull);
+            const unsigned long long s2 = atomicAdd(cursor + c2, 1ull), s3 = atomicAdd(cursor + c3, 1ull);
+            t_indices[s0] = r; t_data[s0] = v0;
+            t_indices[s1] = r; t_data[s1] = v1;
+            t_indices[s2] = r; t_data[s2] = v2;
+            t_indices[s3] = r; t_data[s3] = v3;
+        }
+        for (; k < e; k += 32) {
             const int c = ld_stream(indices + k);
             const float v = ld_stream(data + k);
             const unsigned long long slot = atomicAdd(cursor + c, 1ull);
