@@ -221,16 +221,20 @@ def main():
     kern = {name: [a.elapsed_time(b) for a, b in evs] for name, evs in prof.items()}
     spmm_ms = kern.get("mub_spmm_csr_f32", [])
     P = mu._device.pad_width(min(k + 8, 128))
-    spmm_bytes = 8.0 * nnz + 4.0 * P * (n_local + D)      # 8 B/nnz + dense operands once
+    # one "pass" = one product with A or A^T over all nnz of the shard (A^T runs as several row-panel
+    # launches).  Algorithmic bytes per pass: 8 B/nnz + the dense operands once.
+    pass_bytes = 8.0 * nnz + 4.0 * P * (n_local + D)
+    n_pass = info.passes * args.steps
+    spmm_total = float(np.sum(spmm_ms)) if spmm_ms else float("nan")
     pk, pk_kind = peaks()
     hbm = float(pk.get("hbm_gbs", 6650.0))
-    spmm_avg = float(np.mean(spmm_ms)) if spmm_ms else float("nan")
-    ach = spmm_bytes / (spmm_avg * 1e-3) / 1e9 if spmm_ms else None
+    ach = n_pass * pass_bytes / (spmm_total * 1e-3) / 1e9 if spmm_ms else None
     roofline = {"bound": "hbm", "kernel": f"spmm_csr_rowwarp_kernel<{P}>", "achieved": ach, "peak": hbm,
                 "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None, "peak_kind": pk_kind,
-                "launches": len(spmm_ms), "avg_ms": spmm_avg,
-                "note": "algorithmic bytes = 8 B/nnz + 4*P*(n+D); every nnz also gathers 4*P B of the dense "
-                        "operand through L2->L1, which is the practical limiter (DESIGN.md)"}
+                "launches": len(spmm_ms), "passes": n_pass, "ms_per_pass": spmm_total / max(n_pass, 1),
+                "bytes_per_pass": pass_bytes,
+                "note": "algorithmic bytes = 8 B/nnz + 4*P*(n+D) per pass; every nnz also gathers 4*P B of the dense "
+                        "operand through L2->L1 (ncu: ~80 % of L2 bandwidth), which is the practical limiter (DESIGN.md)"}
     tf_red = kern.get("mub_tfidf_reduce_f32", [])
     tf_app = kern.get("mub_tfidf_apply_f32", [])
     if tf_red and tf_app:

@@ -32,3 +32,11 @@ def all_reduce_max_(t: torch.Tensor) -> torch.Tensor:
     if is_distributed():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     return t
+
+
+def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
+    """Make a replicated tensor bit-identical on every rank (guards the replicated d-space basis
+    against per-process differences in library kernels)."""
+    if is_distributed():
+        torch.distributed.broadcast(t, src=src)
+    return t

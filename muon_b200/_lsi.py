@@ -211,6 +211,9 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
                 Qn, _ = _orth_against(Qn.contiguous(), Vall[:, :m], passes=1)
                 Qn, S2 = _qr_dspace(op, Qn, P)
                 Sj = (S2.to(f64) @ S1.to(f64))          # W = Qn Sj   (bj x bj)
+                if _dist.is_distributed():               # keep the replicated basis bit-identical
+                    Qn = _dist.broadcast_(Qn.contiguous())
+                    Sj = _dist.broadcast_(Sj.contiguous())
             # ---- Rayleigh-Ritz on the block-bidiagonal B (fp64, tiny) ---------------------
             with phase("lsi.ritz_svd"):
                 X, sig, Zt = torch.linalg.svd(Bmat[:m, :m])
@@ -219,6 +222,8 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
                 res = torch.linalg.norm(Sj @ X[j0:j1, :kk], dim=0) / sig[:kk].clamp_min(1e-300)
             else:
                 res = torch.zeros(kk, dtype=f64, device=dev)
+            if _dist.is_distributed():                   # one rank decides: control flow must not diverge
+                res = _dist.broadcast_(res.contiguous())
             rmax = float(res.max())
             info.iterations += 1
             info.history.append(rmax)

@@ -168,8 +168,10 @@ def test_canonical_input_never_takes_the_host_fallback(cuda, monkeypatch):
     got = mu.atac.pp.tfidf(SimpleAnnData(X.copy()), inplace=False)
     assert not calls
     _assert_parity(got, tfidf_ref(X), RTOL32)
-    Xu = X.copy()
-    Xu.indices[X.indptr[130]:X.indptr[130] + 2] = Xu.indices[X.indptr[130]:X.indptr[130] + 2][::-1].copy()
+    Xu = X.copy()                                        # same matrix, two entries of row 130 stored out of order
+    a = X.indptr[130]
+    Xu.indices[a:a + 2] = X.indices[a:a + 2][::-1].copy()
+    Xu.data[a:a + 2] = X.data[a:a + 2][::-1].copy()
     Xu.has_sorted_indices = False
     got = mu.atac.pp.tfidf(SimpleAnnData(Xu), inplace=False)
     assert calls
