@@ -54,20 +54,30 @@ struct PanelCfg {
     static constexpr int ROWS = WARPS * 32;                     // rows per CTA block
 };
 
+// explicit shared-space loads (32-bit addresses): keeps the inner loop on LDS instead of generic LD
+__device__ __forceinline__ int4 lds_v4(uint32_t addr) {
+    int4 r;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
 template <int VEC>
-__device__ __forceinline__ void fma_row(float (&acc)[VEC], float v, const float* __restrict__ brow) {
+__device__ __forceinline__ void fma_lds(float (&acc)[VEC], float v, uint32_t addr) {
     if constexpr (VEC == 1) {
-        acc[0] = fmaf(v, brow[0], acc[0]);
+        float b;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(addr));
+        acc[0] = fmaf(v, b, acc[0]);
     } else if constexpr (VEC == 2) {
-        const float2 b = *reinterpret_cast<const float2*>(brow);
-        acc[0] = fmaf(v, b.x, acc[0]);
-        acc[1] = fmaf(v, b.y, acc[1]);
+        float b0, b1;
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(b0), "=f"(b1) : "r"(addr));
+        acc[0] = fmaf(v, b0, acc[0]);
+        acc[1] = fmaf(v, b1, acc[1]);
     } else {
-        const float4 b = *reinterpret_cast<const float4*>(brow);
-        acc[0] = fmaf(v, b.x, acc[0]);
-        acc[1] = fmaf(v, b.y, acc[1]);
-        acc[2] = fmaf(v, b.z, acc[2]);
-        acc[3] = fmaf(v, b.w, acc[3]);
+        float b0, b1, b2, b3;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(addr));
+        acc[0] = fmaf(v, b0, acc[0]);
+        acc[1] = fmaf(v, b1, acc[1]);
+        acc[2] = fmaf(v, b2, acc[2]);
+        acc[3] = fmaf(v, b3, acc[3]);
     }
 }
 
@@ -83,6 +93,9 @@ spmm_csr_panel_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
     buf[0] = reinterpret_cast<float*>(smem_raw);
     buf[1] = buf[0] + (size_t)panel_cols * P;
     uint64_t* full = reinterpret_cast<uint64_t*>(buf[1] + (size_t)panel_cols * P);
+    // per-warp staging of one row segment: 2 x 32 entries of {byte offset of the B row in the panel, value}
+    int2* stage_all = reinterpret_cast<int2*>(full + 2);
+    const uint32_t buf_u32[2] = {smem_u32(buf[0]), smem_u32(buf[1])};
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_panels = (n_cols + panel_cols - 1) / panel_cols;
@@ -121,6 +134,7 @@ spmm_csr_panel_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
         const int32_t* idx = indices + blk_first;
         const float* val = data + blk_first;
 
+        int2* my_stage = stage_all + warp * 64;
         float acc[32][VEC];
 #pragma unroll
         for (int r = 0; r < 32; ++r)
@@ -134,7 +148,7 @@ spmm_csr_panel_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
         for (int p = 0; p < n_panels; ++p) {
             const int j0 = p * panel_cols;
             const int j1 = (j0 + panel_cols < n_cols) ? j0 + panel_cols : n_cols;
-            const float* panel = buf[consumed & 1] + lane * VEC - (size_t)j0 * P;
+            const uint32_t panel = buf_u32[consumed & 1] + lane * VEC * 4;
             mbar_wait(&full[consumed & 1], (consumed >> 1) & 1);
 
             // software pipeline: row r+1's first 32 candidates are loaded while row r is consumed
@@ -156,41 +170,26 @@ spmm_csr_panel_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
                     nv = (nk < ne) ? ld_stream(val + nk) : 0.f;
                 }
                 for (;;) {
-                    const unsigned m = __ballot_sync(0xffffffffu, c < j1);
+                    const bool inp = c < j1;
+                    const unsigned m = __ballot_sync(0xffffffffu, inp);
                     const int cnt = __popc(m);  // sorted row: in-panel entries are a prefix
-                    // batches of 4 non-zeros: shuffles and shared-memory loads of a batch are issued
-                    // back to back (ILP), then the FMAs; the last batch is padded with zero weights
+                    // stage the segment in this warp's shared scratch (zero weight beyond cnt) and read it
+                    // back by broadcast: no shuffles, hence no per-shuffle convergence barriers
+                    int2* st = my_stage + ((r & 1) << 5);
+                    st[lane] = make_int2(inp ? (c - j0) * (P * 4) : 0, inp ? __float_as_int(v) : 0);
+                    __syncwarp();
+                    const uint32_t st_u32 = smem_u32(st);
                     for (int t = 0; t < cnt; t += 4) {
-                        int cc[4];
-                        float vv[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int src = t + u;
-                            cc[u] = __shfl_sync(0xffffffffu, c, src & 31);
-                            vv[u] = __shfl_sync(0xffffffffu, v, src & 31);
-                            if (src >= cnt) { cc[u] = j0; vv[u] = 0.f; }
-                        }
-                        float bb[4][VEC];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float* br = panel + (size_t)cc[u] * P;
-                            if constexpr (VEC == 1) {
-                                bb[u][0] = br[0];
-                            } else if constexpr (VEC == 2) {
-                                const float2 q = *reinterpret_cast<const float2*>(br);
-                                bb[u][0] = q.x; bb[u][1] = q.y;
-                            } else {
-                                const float4 q = *reinterpret_cast<const float4*>(br);
-                                bb[u][0] = q.x; bb[u][1] = q.y; bb[u][2] = q.z; bb[u][3] = q.w;
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int e = 0; e < VEC; ++e) acc[r][e] = fmaf(vv[u], bb[u][e], acc[r][e]);
+                        const int4 e01 = lds_v4(st_u32 + t * 8);
+                        const int4 e23 = lds_v4(st_u32 + t * 8 + 16);
+                        fma_lds<VEC>(acc[r], __int_as_float(e01.y), panel + e01.x);
+                        fma_lds<VEC>(acc[r], __int_as_float(e01.w), panel + e01.z);
+                        fma_lds<VEC>(acc[r], __int_as_float(e23.y), panel + e23.x);
+                        fma_lds<VEC>(acc[r], __int_as_float(e23.w), panel + e23.z);
                     }
                     base += cnt;
                     if (cnt < 32) break;
+                    __syncwarp();
                     const int k = base + lane;  // a full warp-load was inside the panel: keep going
                     c = (k < rend) ? ld_stream(idx + k) : 0x7fffffff;
                     v = (k < rend) ? ld_stream(val + k) : 0.f;
@@ -229,12 +228,12 @@ static int launch_panel(const int64_t* indptr, const int32_t* indices, const flo
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int budget = max_smem - 1024;                       // barriers + alignment slack
+    const int budget = max_smem - 1024 - Cfg::WARPS * 64 * 8;  // barriers, per-warp staging, slack
     int panel_cols = (budget / 2) / (P * (int)sizeof(float));
     panel_cols &= ~7;
     if (panel_cols > n_cols) panel_cols = (n_cols + 7) & ~7;
     if (panel_cols < 8) panel_cols = 8;
-    const size_t smem = (size_t)2 * panel_cols * P * sizeof(float) + 64;
+    const size_t smem = (size_t)2 * panel_cols * P * sizeof(float) + 64 + (size_t)Cfg::WARPS * 64 * 8;
     cudaError_t e = cudaFuncSetAttribute(spmm_csr_panel_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("spmm_csr_panel: cudaFuncSetAttribute(%zu B smem): %s", smem, cudaGetErrorString(e));
