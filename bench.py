@@ -235,6 +235,14 @@ def main():
                 "bytes_per_pass": pass_bytes,
                 "note": "algorithmic bytes = 8 B/nnz + 4*P*(n+D) per pass; every nnz also gathers 4*P B of the dense "
                         "operand through L2->L1 (ncu: ~80 % of L2 bandwidth), which is the practical limiter (DESIGN.md)"}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        key = f"spmm_rowwarp{P}_n{n_local}_d{D}"
+        if key in tr:
+            roofline["traffic"] = tr[key]["dram_bytes_per_pass"]
+            roofline["traffic_source"] = tr[key]["source"]
+    except Exception:
+        pass
     tf_red = kern.get("mub_tfidf_reduce_f32", [])
     tf_app = kern.get("mub_tfidf_apply_f32", [])
     if tf_red and tf_app:

@@ -151,50 +151,68 @@ spmm_csr_panel_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
             const uint32_t panel = buf_u32[consumed & 1] + lane * VEC * 4;
             mbar_wait(&full[consumed & 1], (consumed >> 1) & 1);
 
-            // software pipeline: row r+1's first 32 candidates are loaded while row r is consumed
-            int nb = __shfl_sync(0xffffffffu, cur, 0), ne = __shfl_sync(0xffffffffu, end, 0);
-            int nk = nb + lane;
-            int nc = (nk < ne) ? ld_stream(idx + nk) : 0x7fffffff;
-            float nv = (nk < ne) ? ld_stream(val + nk) : 0.f;
+            // software pipeline over groups of G rows: the first 32 candidates (index, value) of the
+            // next G rows are in flight while the current G rows are consumed from registers
+            constexpr int G = 8;
+            int nc[G];
+            float nv[G];
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                int base = nb;
-                const int rend = ne;
-                int c = nc;
-                float v = nv;
-                if (r + 1 < 32) {
-                    nb = __shfl_sync(0xffffffffu, cur, r + 1);
-                    ne = __shfl_sync(0xffffffffu, end, r + 1);
-                    nk = nb + lane;
-                    nc = (nk < ne) ? ld_stream(idx + nk) : 0x7fffffff;
-                    nv = (nk < ne) ? ld_stream(val + nk) : 0.f;
-                }
-                for (;;) {
-                    const bool inp = c < j1;
-                    const unsigned m = __ballot_sync(0xffffffffu, inp);
-                    const int cnt = __popc(m);  // sorted row: in-panel entries are a prefix
-                    // stage the segment in this warp's shared scratch (zero weight beyond cnt) and read it
-                    // back by broadcast: no shuffles, hence no per-shuffle convergence barriers
-                    int2* st = my_stage + ((r & 1) << 5);
-                    st[lane] = make_int2(inp ? (c - j0) * (P * 4) : 0, inp ? __float_as_int(v) : 0);
-                    __syncwarp();
-                    const uint32_t st_u32 = smem_u32(st);
-                    for (int t = 0; t < cnt; t += 4) {
-                        const int4 e01 = lds_v4(st_u32 + t * 8);
-                        const int4 e23 = lds_v4(st_u32 + t * 8 + 16);
-                        fma_lds<VEC>(acc[r], __int_as_float(e01.y), panel + e01.x);
-                        fma_lds<VEC>(acc[r], __int_as_float(e01.w), panel + e01.z);
-                        fma_lds<VEC>(acc[r], __int_as_float(e23.y), panel + e23.x);
-                        fma_lds<VEC>(acc[r], __int_as_float(e23.w), panel + e23.z);
+            for (int i = 0; i < G; ++i) {
+                const int b0 = __shfl_sync(0xffffffffu, cur, i), e0 = __shfl_sync(0xffffffffu, end, i);
+                const int k0 = b0 + lane;
+                nc[i] = (k0 < e0) ? ld_stream(idx + k0) : 0x7fffffff;
+                nv[i] = (k0 < e0) ? ld_stream(val + k0) : 0.f;
+            }
+#pragma unroll
+            for (int g = 0; g < 32 / G; ++g) {
+                int cc[G];
+                float cv[G];
+#pragma unroll
+                for (int i = 0; i < G; ++i) { cc[i] = nc[i]; cv[i] = nv[i]; }
+                if (g + 1 < 32 / G) {
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        const int rn = (g + 1) * G + i;
+                        const int b0 = __shfl_sync(0xffffffffu, cur, rn), e0 = __shfl_sync(0xffffffffu, end, rn);
+                        const int k0 = b0 + lane;
+                        nc[i] = (k0 < e0) ? ld_stream(idx + k0) : 0x7fffffff;
+                        nv[i] = (k0 < e0) ? ld_stream(val + k0) : 0.f;
                     }
-                    base += cnt;
-                    if (cnt < 32) break;
-                    __syncwarp();
-                    const int k = base + lane;  // a full warp-load was inside the panel: keep going
-                    c = (k < rend) ? ld_stream(idx + k) : 0x7fffffff;
-                    v = (k < rend) ? ld_stream(val + k) : 0.f;
                 }
-                if (lane == r) cur = base;
+#pragma unroll
+                for (int i = 0; i < G; ++i) {
+                    const int r = g * G + i;
+                    int base = __shfl_sync(0xffffffffu, cur, r);
+                    const int rend = __shfl_sync(0xffffffffu, end, r);
+                    int c = cc[i];
+                    float v = cv[i];
+                    for (;;) {
+                        const bool inp = c < j1;
+                        const unsigned m = __ballot_sync(0xffffffffu, inp);
+                        const int cnt = __popc(m);  // sorted row: in-panel entries are a prefix
+                        // stage the segment in this warp's shared scratch (zero weight beyond cnt) and read
+                        // it back by broadcast: no shuffles, hence no per-shuffle convergence barriers
+                        int2* st = my_stage + ((r & 1) << 5);
+                        st[lane] = make_int2(inp ? (c - j0) * (P * 4) : 0, inp ? __float_as_int(v) : 0);
+                        __syncwarp();
+                        const uint32_t st_u32 = smem_u32(st);
+                        for (int t = 0; t < cnt; t += 4) {
+                            const int4 e01 = lds_v4(st_u32 + t * 8);
+                            const int4 e23 = lds_v4(st_u32 + t * 8 + 16);
+                            fma_lds<VEC>(acc[r], __int_as_float(e01.y), panel + e01.x);
+                            fma_lds<VEC>(acc[r], __int_as_float(e01.w), panel + e01.z);
+                            fma_lds<VEC>(acc[r], __int_as_float(e23.y), panel + e23.x);
+                            fma_lds<VEC>(acc[r], __int_as_float(e23.w), panel + e23.z);
+                        }
+                        base += cnt;
+                        if (cnt < 32) break;
+                        __syncwarp();
+                        const int k = base + lane;  // a full warp-load was inside the panel: keep going
+                        c = (k < rend) ? ld_stream(idx + k) : 0x7fffffff;
+                        v = (k < rend) ? ld_stream(val + k) : 0.f;
+                    }
+                    if (lane == r) cur = base;
+                }
             }
             ++consumed;
             __syncthreads();  // every warp is done with this buffer
