@@ -123,19 +123,24 @@ int mub_gram_f32(const float* Y, const float* weights, int64_t n, int32_t ld, in
  * fp64 arithmetic on fp32 storage.  Dense operands are row-major with leading dimension ld >= K.
  * Centring is implicit: Praw = Y^T E[Z] of the UN-centred sparse view, mu[D] the feature means
  * (NULL = no centring), zsum[K] = column sums of E[Z]; inv_scale = 1/std for scale_views.
- *   update_w : spike-and-slab weights of one view; ZZ[KxK] = E[Z^T Z] (E[z^2] on the diagonal);
- *              tau[D] = E[tau]; alpha/lnth/ln1mth[K] = E[alpha], E[ln theta], E[ln(1-theta)].
+ *   update_w : spike-and-slab weights of one view over G groups of cells (G=1: no grouping).  Arrays
+ *              carry a leading group dimension: Praw[G][D x ld], mu[G][D], zsum[G][K], inv_scale[G],
+ *              ZZ[G][K x K] (E[Z^T Z] of the group's cells observed in this view, E[z^2] on the
+ *              diagonal), tau[G][D] = E[tau]; alpha/lnth/ln1mth[K] = E[alpha], E[ln theta], E[ln(1-theta)].
  *              W is read (current means) and overwritten; WW = E[(sw)^2], S = q(s=1),
  *              What2 = E[what^2] (both branches) are written.
- *   update_z : factors; Q = sum_m Y_m (tau*W_m) un-centred, qshift[K] its centring correction,
- *              GW[KxK] = sum_m W^T diag(tau) W, zvar[K] = Var[z_k].  Z read and overwritten.
- *   tau      : b_out[D] = b0 + 1/2 E||y_d - Z w_d||^2 from ssq[D] (centred sum of squares). */
-int mub_mofa_update_w_f32(const float* Praw, const float* mu, const double* zsum, double inv_scale,
+ *   update_z : factors; Q = sum_m Y_m (tau*W_m) un-centred, and per cell class c (group x set of views
+ *              the cell is observed in; cls[N] or NULL = one class): qshift[C][K] the centring correction,
+ *              GW[C][K x K] = sum_m W^T diag(tau) W, zvar[C][K] = Var[z_k].  Z read and overwritten.
+ *   tau      : b_out[D] = b0 + 1/2 E||y_d - Z w_d||^2 from ssq[D] (centred sum of squares), one
+ *              (view, group) block per call. */
+int mub_mofa_update_w_f32(const float* Praw, const float* mu, const double* zsum, const double* inv_scale,
                           const double* ZZ, const float* tau, const double* alpha, const double* lnth,
                           const double* ln1mth, float* W, float* WW, float* S, float* What2, int64_t D,
-                          int32_t ld, int32_t K, int32_t spikeslab, mub_stream_t stream);
-int mub_mofa_update_z_f32(const float* Q, const double* qshift, const double* GW, const double* zvar, float* Z,
-                          int64_t N, int32_t ld, int32_t K, mub_stream_t stream);
+                          int32_t ld, int32_t K, int32_t G, int32_t spikeslab, mub_stream_t stream);
+int mub_mofa_update_z_f32(const float* Q, const double* qshift, const double* GW, const double* zvar,
+                          const int32_t* cls, float* Z, int64_t N, int32_t ld, int32_t K, int32_t C,
+                          mub_stream_t stream);
 int mub_mofa_tau_f32(const float* Praw, const float* mu, const double* zsum, double inv_scale, const double* ZZ,
                      const double* ssq, const float* W, const float* WW, double b0, double* b_out, int64_t D,
                      int32_t ld, int32_t K, mub_stream_t stream);

@@ -288,7 +288,8 @@ class TransposedPanels:
     exceed what stays resident in L2 the gathers fall through to HBM, so the cells are cut into
     panels whose slice of Y fits in L2 and the products are accumulated panel by panel."""
 
-    L2_BUDGET = 64 << 20   # bytes of the gathered operand per panel (B200 L2: 126 MB)
+    # bytes of the gathered operand per panel (B200 L2: 126 MB, shared with the CSR stream)
+    L2_BUDGET = int(os.environ.get("MUON_B200_L2_BUDGET_MB", "64")) << 20
 
     def __init__(self, A: DeviceCSR, pad: int = 64):
         n = A.shape[0]

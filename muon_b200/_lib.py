@@ -36,8 +36,8 @@ SIGNATURES = {
     "mub_csr_transpose_fill": [vp, vp, vp, i64, i32, i64, vp, vp, vp, vp, vp],
     "mub_gram_f32": [vp, vp, i64, i32, i32, vp, vp, vp],
     "mub_csr_row_stats_f32": [vp, vp, i64, vp, vp, vp],
-    "mub_mofa_update_w_f32": [vp, vp, vp, f64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp],
-    "mub_mofa_update_z_f32": [vp, vp, vp, vp, vp, i64, i32, i32, vp],
+    "mub_mofa_update_w_f32": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],
+    "mub_mofa_update_z_f32": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp],
     "mub_mofa_tau_f32": [vp, vp, vp, f64, vp, vp, vp, vp, f64, vp, i64, i32, i32, vp],
     "mub_synth_count": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp],
     "mub_synth_fill": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp, vp, vp],

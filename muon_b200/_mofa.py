@@ -36,43 +36,71 @@ TOLERANCE = {"fast": 5e-4, "medium": 5e-5, "slow": 5e-6}
 f64 = torch.float64
 
 
-class _View:
-    """One modality on the device: CSR, its transpose, feature moments and variational state."""
+class _Block:
+    """One (view, group) block: the cells of group g observed in view m, as a compact CSR with its
+    transpose panels, plus where those cells sit in the local factor matrix."""
 
-    def __init__(self, A: _device.DeviceCSR, K: int, ld: int, n_total: int, center: bool, scale: bool):
-        dev = A.data.device
+    def __init__(self, A: _device.DeviceCSR, rows, lo: int, hi: int, ld: int):
         self.A, self.At = A, A.transpose_panels(ld)
-        self.D = A.shape[1]
-        D = self.D
-        s1 = torch.empty(D, dtype=f64, device=dev)
-        s2 = torch.empty(D, dtype=f64, device=dev)
-        for i, (_, _, T) in enumerate(self.At.panels):
-            t1, t2 = (s1, s2) if i == 0 else (torch.empty_like(s1), torch.empty_like(s2))
-            call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
-            if i:
-                s1 += t1
-                s2 += t2
+        self.rows, self.lo, self.hi = rows, lo, hi      # rows: LongTensor into local Z, or None = Z[lo:hi]
+        self.n_local = A.shape[0]
+
+    def take(self, Z):                                   # rows of Z belonging to this block (contiguous n x ld)
+        return Z[self.lo:self.hi] if self.rows is None else Z.index_select(0, self.rows)
+
+
+class _View:
+    """One modality: blocks per group, per-(group, feature) moments, variational state of W / alpha / theta / tau."""
+
+    def __init__(self, blocks, D: int, K: int, ld: int, center: bool, scale_views: bool, scale_groups: bool, dev):
+        self.blocks, self.D, self.G = blocks, D, len(blocks)
+        G = self.G
+        s1 = torch.zeros((G, D), dtype=f64, device=dev)
+        s2 = torch.zeros((G, D), dtype=f64, device=dev)
+        cnt = torch.zeros(G, dtype=f64, device=dev)
+        for g, b in enumerate(blocks):
+            cnt[g] = b.n_local
+            if b.n_local == 0:
+                continue
+            for (_, _, T) in b.At.panels:
+                t1, t2 = torch.empty(D, dtype=f64, device=dev), torch.empty(D, dtype=f64, device=dev)
+                call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
+                s1[g] += t1
+                s2[g] += t2
         _dist.all_reduce_sum_(s1)
         _dist.all_reduce_sum_(s2)
-        self.mean = s1 / n_total                                   # intercepts, tools.py:283-286
+        _dist.all_reduce_sum_(cnt)
+        self.n = cnt                                                # cells per group observed in this view (global)
+        nn = cnt.clamp_min(1.0)[:, None]
+        self.mean = s1 / nn                                        # intercepts per group, tools.py:283-286
         mu = self.mean if center else torch.zeros_like(self.mean)
-        ssq = (s2 - 2.0 * mu * s1 + n_total * mu * mu).clamp_min(0)  # sum_n (y - mu)^2
-        self.mu32 = mu.to(torch.float32) if center else None
+        ssq = (s2 - 2.0 * mu * s1 + cnt[:, None] * mu * mu).clamp_min(0)      # sum_n (y - mu)^2 per (g, d)
+        tot = s1 - cnt[:, None] * mu                               # sum_n (y - mu)
+        self.mu32 = mu.to(torch.float32).contiguous() if center else None
         self.mu64 = mu
-        self.inv_scale = 1.0
-        if scale:                                                  # scale_views: global std of the centred view
-            std = float(torch.sqrt(ssq.sum() / (float(n_total) * D)))
-            self.inv_scale = 1.0 / std if std > 0 else 1.0
-        self.ssq = ssq * self.inv_scale ** 2
+        inv = torch.ones(G, dtype=f64, device=dev)
+        if scale_views:                                            # global std of the (centred) view
+            nel = cnt.sum() * D
+            var = ssq.sum() / nel - (tot.sum() / nel) ** 2
+            inv[:] = 1.0 / torch.sqrt(var) if float(var) > 0 else 1.0
+        if scale_groups:                                           # per-group std (takes precedence)
+            nel = (cnt * D).clamp_min(1.0)
+            var = ssq.sum(1) / nel - (tot.sum(1) / nel) ** 2
+            inv = torch.where(var > 0, 1.0 / torch.sqrt(var.clamp_min(1e-300)), torch.ones_like(var))
+        self.inv_scale = inv.contiguous()
+        self.ssq = (ssq * (inv ** 2)[:, None]).contiguous()
         z = lambda: torch.zeros((D, ld), dtype=torch.float32, device=dev)  # noqa: E731
         self.W, self.WW, self.S, self.What2 = z(), z(), z(), z()
         self.S[:, :K] = 1.0
         self.What2[:, :K] = 1.0
-        one = lambda n: torch.ones(n, dtype=f64, device=dev)       # noqa: E731
+        one = lambda *sh: torch.ones(sh, dtype=f64, device=dev)    # noqa: E731
         self.alpha = (one(K), one(K))
         self.theta = (one(K), torch.full((K,), 1e-8, dtype=f64, device=dev))
-        self.tau = (one(D), one(D))
-        self.P = None                                              # Y^T E[Z], un-centred, allreduced
+        self.tau = (one(G, D), one(G, D))
+        self.P = torch.zeros((G, D, ld), dtype=torch.float32, device=dev)   # Y^T E[Z] per group, un-centred
+        self.ZZ = torch.zeros((G, K, K), dtype=f64, device=dev)            # E[Z^T Z] over the block's cells
+        self.ZZ_mean = torch.zeros((G, K, K), dtype=f64, device=dev)
+        self.zsum = torch.zeros((G, K), dtype=f64, device=dev)
 
 
 def _E_gamma(ab):
@@ -107,68 +135,132 @@ def _kl_beta(ab, a0, b0):
 
 
 class MofaDevice:
-    """CAVI state machine on the device (single group, gaussian, no missing values)."""
+    """CAVI state machine on the device: gaussian views, G groups of cells, cells may be missing from
+    whole views (the reference's ``use_obs="union"``), cell-sharded across ranks.
 
-    def __init__(self, views, K, n_total, Z0, center=True, scale_views=False, ard_weights=True, ard_factors=True,
-                 spikeslab_weights=True):
-        self.K, self.N = int(K), int(n_total)
-        self.ld = _device.pad_width(K)
+    ``blocks[m][g]`` = (DeviceCSR of the local cells of group g observed in view m, rows) where ``rows`` is a
+    LongTensor of positions in the local factor matrix or a (lo, hi) range.  ``group_ranges[g]`` = (lo, hi) of
+    group g in the local cell order (cells are ordered by group, as the reference does, tools.py:243-255);
+    ``cls`` = int32 class id per local cell = g * 2^M + bitmask of the views it is observed in (None: all
+    cells in class (0, all views)); ``n_groups_total[g]`` = global number of cells of group g.
+    """
+
+    def __init__(self, blocks, dims, group_ranges, n_groups_total, cls, K, Z0, center=True, scale_views=False,
+                 scale_groups=False, ard_weights=True, ard_factors=True, spikeslab_weights=True):
+        self.K = int(K)
         if K > 64:
             raise NotImplementedError("n_factors > 64 is not supported yet")
+        self.ld = ld = _device.pad_width(K)
+        self.M, self.G = len(blocks), len(group_ranges)
         self.opts = (ard_weights, ard_factors, spikeslab_weights)
-        dev = views[0].data.device
+        dev = Z0.device if Z0.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        self.views = [_View(A, K, self.ld, self.N, center, scale_views) for A in views]
-        self.n_local = views[0].shape[0]
-        self.Z = torch.zeros((self.n_local, self.ld), dtype=torch.float32, device=dev)
+        self.group_ranges = group_ranges
+        self.n_local = group_ranges[-1][1]
+        self.Ng = torch.tensor([float(x) for x in n_groups_total], dtype=f64, device=dev)
+        self.N = int(sum(n_groups_total))
+        self.C = self.G << self.M
+        self.cls = cls
+        # how many cells of class c each (view, group) block / each group holds (global): for sums of Var[z]
+        counts = torch.zeros(self.C, dtype=f64, device=dev)
+        if cls is None:
+            for g, (lo, hi) in enumerate(group_ranges):
+                counts[(g << self.M) | ((1 << self.M) - 1)] = hi - lo
+        else:
+            counts += torch.bincount(cls.to(torch.int64), minlength=self.C).to(f64)
+        self.class_count = _dist.all_reduce_sum_(counts)
+        self.views = []
+        for m in range(self.M):
+            bl = []
+            for g in range(self.G):
+                A, rows = blocks[m][g]
+                if isinstance(rows, tuple):
+                    bl.append(_Block(A, None, rows[0], rows[1], ld))
+                else:
+                    bl.append(_Block(A, rows, 0, 0, ld))
+            self.views.append(_View(bl, dims[m], K, ld, center, scale_views, scale_groups, dev))
+        self.Z = torch.zeros((self.n_local, ld), dtype=torch.float32, device=dev)
         self.Z[:, :K] = Z0.to(dev, torch.float32)
-        self.zvar = torch.ones(K, dtype=f64, device=dev)
-        self.alphaZ = (torch.ones(K, dtype=f64, device=dev), torch.ones(K, dtype=f64, device=dev))
+        self.zvar = torch.ones((self.C, K), dtype=f64, device=dev)
+        self.alphaZ = (torch.ones((self.G, K), dtype=f64, device=dev), torch.ones((self.G, K), dtype=f64, device=dev))
         self.elbo = []
         self._stats_Z()
 
-    # -- sufficient statistics of Z: two sparse passes (one per view) + Gram ---------------------------------
+    def _class_members(self, m, g):
+        """class ids of group g whose cells are observed in view m"""
+        return [(g << self.M) | bits for bits in range(1 << self.M) if bits & (1 << m)]
+
+    # -- sufficient statistics of Z: one transposed sparse pass per (view, group) block + Grams -----------------
     def _stats_Z(self):
         K = self.K
-        ZZ = _device.gram(self.Z, K, reduce=True)
-        self.ZZ_mean = ZZ.clone()
-        ZZ[range(K), range(K)] += self.N * self.zvar
-        self.ZZ = ZZ.contiguous()
-        self.zsum = _dist.all_reduce_sum_(self.Z[:, :K].sum(0, dtype=f64)).contiguous()
-        for v in self.views:
-            v.P = _dist.all_reduce_sum_(v.At.spmm(self.Z, dynamic=True))
+        dK = torch.arange(K, device=self.dev)
+        for m, v in enumerate(self.views):
+            for g, b in enumerate(v.blocks):
+                if b.n_local > 0:
+                    Zb = b.take(self.Z)
+                    ZZ = _device.gram(Zb, K, reduce=False)
+                    zs = Zb[:, :K].sum(0, dtype=f64)
+                    P = b.At.spmm(Zb.contiguous(), dynamic=True)
+                else:
+                    ZZ = torch.zeros((K, K), dtype=f64, device=self.dev)
+                    zs = torch.zeros(K, dtype=f64, device=self.dev)
+                    P = torch.zeros((v.D, self.ld), dtype=torch.float32, device=self.dev)
+                v.ZZ_mean[g], v.zsum[g], v.P[g] = ZZ, zs, P
+            _dist.all_reduce_sum_(v.ZZ_mean)
+            _dist.all_reduce_sum_(v.zsum)
+            _dist.all_reduce_sum_(v.P)
+            v.ZZ = v.ZZ_mean.clone()
+            for g in range(self.G):
+                cl = self._class_members(m, g)
+                v.ZZ[g, dK, dK] += (self.class_count[cl, None] * self.zvar[cl]).sum(0)
+        # E[z^2] summed over all cells of a group (for AlphaZ)
+        ez2 = torch.zeros((self.G, K), dtype=f64, device=self.dev)
+        for g, (lo, hi) in enumerate(self.group_ranges):
+            if hi > lo:
+                ez2[g] = (self.Z[lo:hi, :K].to(f64) ** 2).sum(0)
+        _dist.all_reduce_sum_(ez2)
+        for g in range(self.G):
+            cl = list(range(g << self.M, (g + 1) << self.M))
+            ez2[g] += (self.class_count[cl, None] * self.zvar[cl]).sum(0)
+        self.Ez2 = ez2
 
     def step(self):
-        K, ld, st = self.K, self.ld, stream_ptr()
+        K, ld, st, G, M, C = self.K, self.ld, stream_ptr(), self.G, self.M, self.C
         ard_w, ard_f, ss = self.opts
         onesK = torch.ones(K, dtype=f64, device=self.dev)
         # ---- W ----------------------------------------------------------------------------------------
         for v in self.views:
-            Etau = _E_gamma(v.tau)[0].to(torch.float32).contiguous()
+            Etau = _E_gamma(v.tau)[0].to(torch.float32).contiguous()              # G x D
             Ea = (_E_gamma(v.alpha)[0] if ard_w else onesK).contiguous()
             lnth, ln1mth = _E_beta(v.theta)
-            call("mub_mofa_update_w_f32", ptr(v.P), ptr(v.mu32), ptr(self.zsum), v.inv_scale, ptr(self.ZZ), ptr(Etau),
+            call("mub_mofa_update_w_f32", ptr(v.P), ptr(v.mu32), ptr(v.zsum), ptr(v.inv_scale), ptr(v.ZZ), ptr(Etau),
                  ptr(Ea), ptr(lnth.contiguous()), ptr(ln1mth.contiguous()), ptr(v.W), ptr(v.WW), ptr(v.S),
-                 ptr(v.What2), v.D, ld, K, 1 if ss else 0, st)
+                 ptr(v.What2), v.D, ld, K, G, 1 if ss else 0, st)
             v.Etau32 = Etau
         # ---- Z ----------------------------------------------------------------------------------------
-        Q = None
-        GW = torch.zeros((K, K), dtype=f64, device=self.dev)
-        cW = torch.zeros(K, dtype=f64, device=self.dev)
-        qshift = torch.zeros(K, dtype=f64, device=self.dev)
-        for v in self.views:
-            tw = (v.W * (v.Etau32 * v.inv_scale)[:, None]).contiguous()        # D x ld operand of the SpMM
-            if Q is None:
-                Q = _device.spmm(v.A, tw, dynamic=False)
-            else:
-                _device.spmm(v.A, tw, out=Q, accumulate=True, dynamic=False)
-            qshift += (v.mu64[:, None] * tw[:, :K].to(f64)).sum(0) if v.mu32 is not None else 0.0
-            GW += _device.gram(v.W, K, weights=v.Etau32, reduce=False)
-            cW += v.Etau32.to(f64) @ v.WW[:, :K].to(f64)
-        EaZ = _E_gamma(self.alphaZ)[0] if ard_f else onesK
-        self.zvar = (1.0 / (EaZ + cW)).contiguous()
+        Q = torch.zeros((self.n_local, ld), dtype=torch.float32, device=self.dev)
+        GW = torch.zeros((C, K, K), dtype=f64, device=self.dev)
+        cW = torch.zeros((C, K), dtype=f64, device=self.dev)
+        qshift = torch.zeros((C, K), dtype=f64, device=self.dev)
+        for m, v in enumerate(self.views):
+            for g, b in enumerate(v.blocks):
+                tw = (v.W * (v.Etau32[g] * v.inv_scale[g].to(torch.float32))[:, None]).contiguous()   # D x ld operand
+                if b.n_local > 0:
+                    if b.rows is None:
+                        _device.spmm(b.A, tw, out=Q[b.lo:b.hi], accumulate=True, dynamic=False)
+                    else:
+                        Q.index_add_(0, b.rows, _device.spmm(b.A, tw, dynamic=False))
+                qs = (v.mu64[g][:, None] * tw[:, :K].to(f64)).sum(0) if v.mu32 is not None else 0.0
+                gw = _device.gram(v.W, K, weights=v.Etau32[g].contiguous(), reduce=False)
+                cw = v.Etau32[g].to(f64) @ v.WW[:, :K].to(f64)
+                for c in self._class_members(m, g):
+                    GW[c] += gw
+                    cW[c] += cw
+                    qshift[c] += qs
+        EaZ = _E_gamma(self.alphaZ)[0] if ard_f else torch.ones((G, K), dtype=f64, device=self.dev)
+        self.zvar = (1.0 / (EaZ.repeat_interleave(1 << M, dim=0) + cW)).contiguous()
         call("mub_mofa_update_z_f32", ptr(Q), ptr(qshift.contiguous()), ptr(GW.contiguous()), ptr(self.zvar),
-             ptr(self.Z), self.n_local, ld, K, st)
+             ptr(self.cls), ptr(self.Z), self.n_local, ld, K, C, st)
         del Q
         self._stats_Z()
         # ---- AlphaW, ThetaW, AlphaZ ---------------------------------------------------------------------
@@ -180,25 +272,26 @@ class MofaDevice:
                 s1 = v.S[:, :K].sum(0, dtype=f64)
                 v.theta = (TH_A0 + s1, TH_B0 + v.D - s1)
         if ard_f:
-            self.alphaZ = (torch.full((K,), A0 + 0.5 * self.N, dtype=f64, device=self.dev),
-                           B0 + 0.5 * torch.diagonal(self.ZZ).clone())
+            self.alphaZ = ((A0 + 0.5 * self.Ng)[:, None].expand(G, K).contiguous(), B0 + 0.5 * self.Ez2)
         # ---- Tau ----------------------------------------------------------------------------------------
         for v in self.views:
-            b = torch.empty(v.D, dtype=f64, device=self.dev)
-            call("mub_mofa_tau_f32", ptr(v.P), ptr(v.mu32), ptr(self.zsum), v.inv_scale, ptr(self.ZZ), ptr(v.ssq),
-                 ptr(v.W), ptr(v.WW), B0, ptr(b), v.D, ld, K, st)
-            v.tau = (torch.full((v.D,), A0 + 0.5 * self.N, dtype=f64, device=self.dev), b)
+            b = torch.empty((G, v.D), dtype=f64, device=self.dev)
+            for g in range(G):
+                call("mub_mofa_tau_f32", ptr(v.P[g]), ptr(v.mu32[g]) if v.mu32 is not None else None, ptr(v.zsum[g]),
+                     float(v.inv_scale[g]), ptr(v.ZZ[g]), ptr(v.ssq[g]), ptr(v.W), ptr(v.WW), B0, ptr(b[g]), v.D, ld,
+                     K, st)
+            v.tau = ((A0 + 0.5 * v.n)[:, None].expand(G, v.D).contiguous(), b)
         self.elbo.append(self._elbo())
 
     def _elbo(self):
-        """Same expression as oracle/mofa_ref.py::elbo (tau trick; valid right after the Tau update)."""
-        K, N = self.K, self.N
+        """Same expression as oracle/mofa_ref.py (tau trick; valid right after the Tau update)."""
+        K, G, M = self.K, self.G, self.M
         ard_w, ard_f, ss = self.opts
         total = 0.0
         two_pi = 2.0 * np.pi
         for v in self.views:
             Etau, Elntau = _E_gamma(v.tau)
-            total += float((0.5 * N * (Elntau - np.log(two_pi)) - Etau * (v.tau[1] - B0)).sum())
+            total += float((0.5 * v.n[:, None] * (Elntau - np.log(two_pi)) - Etau * (v.tau[1] - B0)).sum())
             total += _kl_gamma(v.tau, A0, B0)
             if ard_w:
                 Ea, Elna = _E_gamma(v.alpha)
@@ -223,34 +316,35 @@ class MofaDevice:
         if ard_f:
             Ea, Elna = _E_gamma(self.alphaZ)
         else:
-            Ea, Elna = torch.ones(K, dtype=f64, device=self.dev), torch.zeros(K, dtype=f64, device=self.dev)
-        Ez2 = torch.diagonal(self.ZZ)
-        total += float((0.5 * N * Elna - 0.5 * Ea * Ez2 + 0.5 * N + 0.5 * N * torch.log(self.zvar)).sum())
+            Ea, Elna = (torch.ones((G, K), dtype=f64, device=self.dev), torch.zeros((G, K), dtype=f64, device=self.dev))
+        total += float((0.5 * self.Ng[:, None] * Elna - 0.5 * Ea * self.Ez2 + 0.5 * self.Ng[:, None]).sum())
+        total += float((0.5 * self.class_count[:, None] * torch.log(self.zvar)).sum())
         if ard_f:
             total += _kl_gamma(self.alphaZ, A0, B0)
         return total
 
     def variance_explained(self):
-        """R^2 (%) per view and factor from sufficient statistics: 1 - SS(Y - z_k w_k^T)/SS(Y)."""
+        """R^2 (%) per view, group and factor from sufficient statistics: 1 - SS(Y - z_k w_k^T)/SS(Y)."""
         K = self.K
         out = []
-        zz = torch.diagonal(self.ZZ_mean)
         for v in self.views:
             W = v.W[:, :K].to(f64)
-            P = (v.P[:, :K].to(f64) - (v.mu64[:, None] * self.zsum[None, :] if v.mu32 is not None else 0.0)) * v.inv_scale
-            ss = v.ssq.sum()
-            res = ss - 2.0 * (W * P).sum(0) + (W * W).sum(0) * zz
-            out.append(100.0 * (1.0 - res / ss))
+            r2 = torch.zeros((self.G, K), dtype=f64, device=self.dev)
+            for g in range(self.G):
+                P = v.P[g][:, :K].to(f64)
+                if v.mu32 is not None:
+                    P = P - v.mu64[g][:, None] * v.zsum[g][None, :]
+                P = P * v.inv_scale[g]
+                ss = v.ssq[g].sum()
+                res = ss - 2.0 * (W * P).sum(0) + (W * W).sum(0) * torch.diagonal(v.ZZ_mean[g])
+                r2[g] = 100.0 * (1.0 - res / ss) if float(ss) > 0 else 0.0
+            out.append(r2)
         return out
 
 
-def run_mofa_device(views, n_factors, n_iterations, n_total, Z0, center=True, scale_views=False, ard_weights=True,
-                    ard_factors=True, spikeslab_weights=True, convergence_mode="fast", check_convergence=True,
-                    sort_factors=True, verbose=False):
-    """Train on device-resident views; returns dict(Z, W (list), variance (list), elbo, iterations, converged)."""
-    model = MofaDevice(views, n_factors, n_total, Z0, center, scale_views, ard_weights, ard_factors, spikeslab_weights)
+def _train(model, n_iterations, convergence_mode, check_convergence, sort_factors, verbose):
     tol = TOLERANCE[convergence_mode]
-    converged, it = False, 0
+    converged, it = False, -1
     for it in range(n_iterations):
         model.step()
         if verbose and _dist.rank() == 0:
@@ -260,14 +354,29 @@ def run_mofa_device(views, n_factors, n_iterations, n_total, Z0, center=True, sc
             if delta < tol:
                 converged = True
                 break
-    var = model.variance_explained()
-    K = n_factors
+    var = model.variance_explained()                       # list over views of G x K
+    K = model.K
     order = torch.arange(K, device=model.dev)
     if sort_factors:
-        order = torch.argsort(-torch.stack(var).sum(0), stable=True)
+        order = torch.argsort(-torch.stack([x.sum(0) for x in var]).sum(0), stable=True)
     return {"Z": model.Z[:, :K][:, order], "W": [v.W[:, :K][:, order] for v in model.views],
-            "variance": [x[order] for x in var], "elbo": model.elbo, "iterations": it + 1 if n_iterations else 0,
+            "variance": [x[:, order] for x in var], "elbo": model.elbo, "iterations": it + 1,
             "converged": converged, "order": order, "intercepts": [v.mean for v in model.views], "model": model}
+
+
+def run_mofa_device(views, n_factors, n_iterations, n_total, Z0, center=True, scale_views=False, ard_weights=True,
+                    ard_factors=True, spikeslab_weights=True, convergence_mode="fast", check_convergence=True,
+                    sort_factors=True, verbose=False):
+    """One group, every cell observed in every view (the benchmark case).  ``views``: DeviceCSR per modality
+    (this rank's cells).  Returns dict(Z, W (list), variance (list of K-vectors), elbo, iterations, converged)."""
+    n_local = views[0].shape[0]
+    blocks = [[(A, (0, n_local))] for A in views]
+    model = MofaDevice(blocks, [A.shape[1] for A in views], [(0, n_local)], [n_total], None, n_factors, Z0, center,
+                       scale_views, False, ard_weights, ard_factors, spikeslab_weights)
+    res = _train(model, n_iterations, convergence_mode, check_convergence, sort_factors, verbose)
+    res["variance"] = [x[0] for x in res["variance"]]
+    res["intercepts"] = [x[0] for x in res["intercepts"]]
+    return res
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -328,6 +437,7 @@ def mofa(
     """
     if is_anndata(data):
         mdata = SimpleMuData({"data": data})            # tools.py:425-431
+        mdata.obs = data.obs
     elif is_mudata(data):
         mdata = data
     else:
@@ -336,6 +446,7 @@ def mofa(
     if use_var and (not hasattr(data.var, "columns") or use_var not in data.var.columns):
         warn(f"There is no column {use_var} in the provided object")     # tools.py:438-440
         use_var = None
+    common_obs = None
     if is_mudata(data):
         common_obs = reduce(np.intersect1d, [np.asarray(v.obs_names) for v in mdata.mod.values()])
         if len(common_obs) != mdata.n_obs:
@@ -345,11 +456,11 @@ def mofa(
                     "to subset the data or devise a strategy with `use_obs` ('union' or 'intersection')")
             elif use_obs not in ["union", "intersection"]:
                 raise ValueError(f"Expected `use_obs` argument to be 'union' or 'intersection', not '{use_obs}'")
-            raise NotImplementedError("use_obs='union'/'intersection' (ragged observations) is not supported yet")
-        use_obs = None
+        else:
+            use_obs = None
 
-    for flag, name in ((groups_label, "groups_label"), (svi_mode, "svi_mode"), (smooth_covariate, "smooth_covariate"),
-                       (spikeslab_factors, "spikeslab_factors"), (scale_groups, "scale_groups"), (use_raw, "use_raw")):
+    for flag, name in ((svi_mode, "svi_mode"), (smooth_covariate, "smooth_covariate"),
+                       (spikeslab_factors, "spikeslab_factors"), (use_raw, "use_raw")):
         if flag:
             raise NotImplementedError(f"mofa(..., {name}=...) is not supported by the B200 path yet")
     lik = likelihoods
@@ -357,13 +468,19 @@ def mofa(
         lik = [lik] * len(mdata.mod) if isinstance(lik, str) else list(lik)
         if any(l != "gaussian" for l in lik):
             raise NotImplementedError("only the gaussian likelihood is supported by the B200 path yet")
-    if outfile is not None and not quiet:
-        warn("outfile is ignored: the model is not written to HDF5 (h5py unavailable)")
+    if groups_label is not None and (not hasattr(mdata.obs, "columns") or groups_label not in mdata.obs.columns):
+        raise KeyError(f"{groups_label} is not in observations names")     # reference prints and exits, tools.py:98-101
 
     _device.require_cuda()
-    # ---- marshal modalities (tools.py:104-176), sparse, no densification ---------------------------------
+    import scipy.sparse as sp
+    dev = torch.device("cuda", torch.cuda.current_device())
     mods = list(mdata.mod.keys())
-    views, masks = [], []
+    M = len(mods)
+    obs_all = np.asarray(mdata.obs_names).astype(str)
+    simple = (use_obs is None and groups_label is None and not scale_groups)
+
+    # ---- features (tools.py:172-176) -----------------------------------------------------------------------
+    Xs, masks = [], []
     for m in mods:
         adata = mdata.mod[m]
         X = adata.layers[use_layer] if use_layer else adata.X
@@ -372,26 +489,88 @@ def mofa(
             mask = np.asarray(adata.var[use_var].astype(bool))
             if isinstance(X, _device.DeviceCSR):
                 raise NotImplementedError("use_var with a device-resident matrix is not supported yet")
-            import scipy.sparse as sp
             X = (X.tocsr() if sp.issparse(X) else np.asarray(X))[:, mask]
         elif use_var:
             mask = np.ones(adata.n_vars, dtype=bool)
-        views.append(_to_device_view(X))
+        Xs.append(X)
         masks.append(mask)
-    n_local = views[0].shape[0]
-    n_total = views[0].n_total
-    row0 = views[0].row0
 
-    rs = np.random.RandomState(seed)
-    Z0 = torch.from_numpy(rs.normal(size=(n_total, n_factors))[row0:row0 + n_local])
-    res = run_mofa_device(views, n_factors, n_iterations, n_total, Z0, center=center_groups, scale_views=scale_views,
-                          ard_weights=ard_weights, ard_factors=ard_factors, spikeslab_weights=spikeslab_weights,
-                          convergence_mode=convergence_mode, verbose=verbose and not quiet)
+    if simple:
+        views = [_to_device_view(X) for X in Xs]
+        n_local, n_total, row0 = views[0].shape[0], views[0].n_total, views[0].row0
+        rs = np.random.RandomState(seed)
+        Z0 = torch.from_numpy(rs.normal(size=(n_total, n_factors))[row0:row0 + n_local])
+        res = run_mofa_device(views, n_factors, n_iterations, n_total, Z0, center=center_groups,
+                              scale_views=scale_views, ard_weights=ard_weights, ard_factors=ard_factors,
+                              spikeslab_weights=spikeslab_weights, convergence_mode=convergence_mode,
+                              verbose=verbose and not quiet)
+        Z_full = res["Z"].cpu().numpy()
+        group_names = ["group1"]
+        variance = {m: res["variance"][i].cpu().numpy() for i, m in enumerate(mods)}
+    else:
+        # ---- general path: groups of cells and/or cells missing from whole views (host matrices) ---------------
+        if any(isinstance(X, _device.DeviceCSR) for X in Xs) or _dist.is_distributed():
+            raise NotImplementedError("groups_label / use_obs need host matrices on a single process for now")
+        sel = obs_all if use_obs != "intersection" else obs_all[np.isin(obs_all, common_obs.astype(str))]
+        if groups_label is not None:                       # groups in order of first appearance, tools.py:215-219
+            glab_all = np.asarray(mdata.obs[groups_label]).astype(str)
+            glab = glab_all[np.isin(obs_all, sel)] if len(sel) != len(obs_all) else glab_all
+            group_names = list(dict.fromkeys(glab.tolist()))
+        else:
+            glab = np.array(["group1"] * len(sel))
+            group_names = ["group1"]
+        gid = np.array([group_names.index(x) for x in glab])
+        perm = np.argsort(gid, kind="stable")               # cells ordered by group (tools.py:243-255)
+        cells = sel[perm]
+        gid = gid[perm]
+        N = len(cells)
+        G = len(group_names)
+        bounds = np.searchsorted(gid, np.arange(G + 1))
+        group_ranges = [(int(bounds[g]), int(bounds[g + 1])) for g in range(G)]
+        pos_of = {c: i for i, c in enumerate(cells)}
+        bits = np.zeros(N, dtype=np.int64)
+        blocks, dims = [], []
+        for mi, m in enumerate(mods):
+            names = np.asarray(mdata.mod[m].obs_names).astype(str)
+            X = Xs[mi]
+            X = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
+            here = np.array([pos_of.get(c, -1) for c in names])     # position of each of the view's rows in Z
+            keep = np.nonzero(here >= 0)[0]
+            order = keep[np.argsort(here[keep], kind="stable")]      # view rows in Z order
+            zpos = here[order]
+            bits[zpos] |= (1 << mi)
+            per_g = []
+            for g, (lo, hi) in enumerate(group_ranges):
+                selg = (zpos >= lo) & (zpos < hi)
+                rows_z = zpos[selg]
+                Xg = X[order[selg]].astype(np.float32)
+                A = _device.DeviceCSR.from_scipy(sp.csr_matrix(Xg), dtype=np.float32)
+                if len(rows_z) == hi - lo and np.array_equal(rows_z, np.arange(lo, hi)):
+                    per_g.append((A, (lo, hi)))
+                else:
+                    per_g.append((A, torch.from_numpy(rows_z.astype(np.int64)).to(dev)))
+            blocks.append(per_g)
+            dims.append(X.shape[1])
+        cls = torch.from_numpy(((gid << M) | bits).astype(np.int32)).to(dev)
+        rs = np.random.RandomState(seed)
+        Z0 = torch.from_numpy(rs.normal(size=(N, n_factors)))
+        model = MofaDevice(blocks, dims, group_ranges, [hi - lo for lo, hi in group_ranges], cls, n_factors, Z0,
+                           center_groups, scale_views, scale_groups, ard_weights, ard_factors, spikeslab_weights)
+        res = _train(model, n_iterations, convergence_mode, True, True, verbose and not quiet)
+        Zp = res["Z"].cpu().numpy()
+        where = {c: i for i, c in enumerate(obs_all)}
+        Z_full = np.full((len(obs_all), n_factors), np.nan)          # tools.py:617-622
+        Z_full[[where[c] for c in cells]] = Zp
+        if G > 1:                                                    # tools.py:690-697
+            variance = {m: {group_names[g]: res["variance"][i][g].cpu().numpy() for g in range(G)}
+                        for i, m in enumerate(mods)}
+        else:
+            variance = {m: res["variance"][i][0].cpu().numpy() for i, m in enumerate(mods)}
 
     if copy:
         data = data.copy()
     out_dt = np.float32 if use_float32 else np.float64
-    data.obsm["X_mofa"] = res["Z"].cpu().numpy().astype(out_dt)                       # tools.py:628
+    data.obsm["X_mofa"] = Z_full.astype(out_dt)                                         # tools.py:616-628
     w = np.concatenate([W.cpu().numpy() for W in res["W"]], axis=0).astype(out_dt)
     if use_var:                                                                      # tools.py:636-641
         full = np.zeros((data.n_vars, w.shape[1]), dtype=out_dt)
@@ -410,7 +589,7 @@ def mofa(
             "training": {"n_iterations": n_iterations, "convergence_mode": convergence_mode, "gpu_mode": gpu_mode,
                          "seed": seed},
         },
-        "variance": {m: res["variance"][i].cpu().numpy() for i, m in enumerate(mods)},
+        "variance": variance,
     }
     data.uns["mofa"]["_b200"] = {"iterations": res["iterations"], "converged": res["converged"], "elbo": res["elbo"]}
     if copy:

@@ -263,3 +263,149 @@ def mofa_ref(views, n_factors=10, n_iterations=1000, center=True, scale_views=Fa
         order = np.argsort(-np.sum(var, axis=0), kind="stable")
     return {"Z": st.Z[:, order], "W": [w[:, order] for w in st.W], "variance": [v[order] for v in var],
             "elbo": st.elbo, "order": order, "state": st, "intercepts": means, "scales": scales}
+
+
+# ======================================================================================================
+# General form: groups of cells and missing values, written the textbook way with an explicit N x D mask
+# per view (exactly how the reference feeds mofapy2 after tools.py:144-169 expanded the "union" of
+# observations with NaN rows and tools.py:243-255 ordered the cells by group).  Independent of the
+# sufficient-statistics formulation above and of the CUDA path, which makes it a cross-check for both.
+# ======================================================================================================
+def mofa_ref_general(views, groups=None, n_factors=10, n_iterations=1000, center_groups=True, scale_views=False,
+                     scale_groups=False, ard_weights=True, ard_factors=True, spikeslab_weights=True,
+                     convergence_mode="fast", seed=1, Z0=None, sort_factors=True, check_convergence=True):
+    """``views``: list of N x D_m float arrays with NaN = missing; ``groups``: length-N array of group labels
+    (None = one group).  Returns Z, W, variance[view] -> array (G x K, %), elbo, ..."""
+    Ys = [np.array(Y.todense() if hasattr(Y, "todense") else Y, dtype=np.float64) for Y in views]
+    N = Ys[0].shape[0]
+    M = len(Ys)
+    K = n_factors
+    glab = np.zeros(N, dtype=np.int64) if groups is None else np.unique(np.asarray(groups), return_inverse=True)[1]
+    G = int(glab.max()) + 1
+    gsel = [glab == g for g in range(G)]
+    masks, means, scales = [], [], []
+    for m in range(M):
+        mask = ~np.isnan(Ys[m])
+        Y = np.where(mask, Ys[m], 0.0)
+        mu = np.zeros((G, Y.shape[1]))
+        for g in range(G):
+            cnt = mask[gsel[g]].sum(0)
+            mu[g] = Y[gsel[g]].sum(0) / np.maximum(cnt, 1)
+            if center_groups:
+                Y[gsel[g]] -= mu[g] * mask[gsel[g]]
+        sc = np.ones(G)
+        if scale_views:
+            sc[:] = np.sqrt((Y ** 2).sum() / mask.sum() - (Y.sum() / mask.sum()) ** 2)
+        if scale_groups:
+            for g in range(G):
+                yy, mm = Y[gsel[g]], mask[gsel[g]]
+                sc[g] = np.sqrt((yy ** 2).sum() / mm.sum() - (yy.sum() / mm.sum()) ** 2)
+        for g in range(G):
+            Y[gsel[g]] /= sc[g]
+        Ys[m] = Y
+        masks.append(mask)
+        means.append(mu)
+        scales.append(sc)
+    dims = [Y.shape[1] for Y in Ys]
+    rs = np.random.RandomState(seed)
+    Z = rs.normal(size=(N, K)) if Z0 is None else np.array(Z0, dtype=np.float64)
+    Zvar = np.ones((N, K))
+    W = [np.zeros((D, K)) for D in dims]
+    WW = [np.zeros((D, K)) for D in dims]
+    S = [np.ones((D, K)) for D in dims]
+    What2 = [np.ones((D, K)) for D in dims]
+    alphaW = [(np.ones(K), np.ones(K)) for _ in dims]
+    alphaZ = (np.ones((G, K)), np.ones((G, K)))
+    theta = [(np.ones(K), np.full(K, 1e-8)) for _ in dims]
+    tau = [(np.ones((G, D)), np.ones((G, D))) for D in dims]
+    tol = TOLERANCE[convergence_mode]
+    elbos, converged, it = [], False, -1
+    for it in range(n_iterations):
+        ZZd = Z ** 2 + Zvar
+        for m in range(M):
+            Etau = (tau[m][0] / tau[m][1])[glab] * masks[m]                     # N x D, 0 where missing
+            Ea = alphaW[m][0] / alphaW[m][1] if ard_weights else np.ones(K)
+            lnth, ln1mth = _E_beta(theta[m])
+            for k in range(K):
+                a = Etau.T @ ZZd[:, k] + Ea[k]
+                res = Ys[m] - Z @ W[m].T + np.outer(Z[:, k], W[m][:, k])
+                b = ((Etau * res) * Z[:, [k]]).sum(0)
+                mm_, v = b / a, 1.0 / a
+                s = expit(lnth[k] - ln1mth[k] + 0.5 * np.log(Ea[k]) - 0.5 * np.log(a) + 0.5 * b * b / a) \
+                    if spikeslab_weights else np.ones_like(a)
+                S[m][:, k], W[m][:, k] = s, s * mm_
+                WW[m][:, k] = s * (mm_ * mm_ + v)
+                What2[m][:, k] = WW[m][:, k] + (1.0 - s) / Ea[k]
+        EaZ = (alphaZ[0] / alphaZ[1])[glab] if ard_factors else np.ones((N, K))
+        prec = EaZ.copy()
+        for m in range(M):
+            prec += ((tau[m][0] / tau[m][1])[glab] * masks[m]) @ WW[m]
+        Zvar = 1.0 / prec
+        for k in range(K):
+            b = np.zeros(N)
+            for m in range(M):
+                Etau = (tau[m][0] / tau[m][1])[glab] * masks[m]
+                res = Ys[m] - Z @ W[m].T + np.outer(Z[:, k], W[m][:, k])
+                b += (Etau * res) @ W[m][:, k]
+            Z[:, k] = Zvar[:, k] * b
+        ZZd = Z ** 2 + Zvar
+        for m in range(M):
+            if ard_weights:
+                alphaW[m] = (np.full(K, A0 + 0.5 * dims[m]), B0 + 0.5 * What2[m].sum(0))
+            if spikeslab_weights:
+                s1 = S[m].sum(0)
+                theta[m] = (TH_A0 + s1, TH_B0 + dims[m] - s1)
+        if ard_factors:
+            alphaZ = (np.stack([np.full(K, A0 + 0.5 * gsel[g].sum()) for g in range(G)]),
+                      np.stack([B0 + 0.5 * ZZd[gsel[g]].sum(0) for g in range(G)]))
+        for m in range(M):
+            E2 = (Ys[m] - Z @ W[m].T) ** 2 + ZZd @ WW[m].T - (Z ** 2) @ (W[m] ** 2).T
+            ta = np.stack([A0 + 0.5 * masks[m][gsel[g]].sum(0) for g in range(G)])
+            tb = np.stack([B0 + 0.5 * (E2[gsel[g]] * masks[m][gsel[g]]).sum(0) for g in range(G)])
+            tau[m] = (ta, tb)
+        # ---- ELBO (same terms as ``elbo`` above, per group / per cell) ---------------------------------
+        tot = 0.0
+        for m in range(M):
+            Etau, Elntau = _E_gamma(tau[m])
+            nmg = np.stack([masks[m][gsel[g]].sum(0) for g in range(G)])
+            tot += float(np.sum(0.5 * nmg * (Elntau - np.log(2 * np.pi)) - Etau * (tau[m][1] - B0)))
+            tot += _kl_gamma(tau[m], A0, B0)
+            Ea, Elna = _E_gamma(alphaW[m]) if ard_weights else (np.ones(K), np.zeros(K))
+            Sc = np.clip(S[m], 1e-300, 1.0)
+            lp = -0.5 * np.log(2 * np.pi) + 0.5 * Elna[None, :] - 0.5 * Ea[None, :] * What2[m]
+            var1 = np.maximum(np.where(S[m] > 0, WW[m] / np.maximum(S[m], 1e-300) - (W[m] / np.maximum(S[m], 1e-300)) ** 2, 1.0), 1e-300)
+            ent = Sc * 0.5 * np.log(2 * np.pi * np.e * var1) + (1 - Sc) * 0.5 * np.log(2 * np.pi * np.e / Ea[None, :])
+            tot += float(np.sum(lp + ent))
+            if spikeslab_weights:
+                lnth, ln1mth = _E_beta(theta[m])
+                S1 = np.clip(1 - S[m], 1e-300, 1.0)
+                tot += float(np.sum(S[m] * lnth[None, :] + (1 - S[m]) * ln1mth[None, :] - S[m] * np.log(Sc) - (1 - S[m]) * np.log(S1)))
+                tot += _kl_beta(theta[m], TH_A0, TH_B0)
+            if ard_weights:
+                tot += _kl_gamma(alphaW[m], A0, B0)
+        if ard_factors:
+            EaZg, ElnaZg = _E_gamma(alphaZ)
+        else:
+            EaZg, ElnaZg = np.ones((G, K)), np.zeros((G, K))
+        tot += float(np.sum(0.5 * ElnaZg[glab] - 0.5 * EaZg[glab] * ZZd + 0.5 + 0.5 * np.log(Zvar)))
+        if ard_factors:
+            tot += _kl_gamma(alphaZ, A0, B0)
+        elbos.append(tot)
+        if check_convergence and it >= 1 and 100.0 * abs((elbos[-1] - elbos[-2]) / elbos[0]) < tol:
+            converged = True
+            break
+    var = []
+    for m in range(M):
+        r2 = np.zeros((G, K))
+        for g in range(G):
+            mk = masks[m][gsel[g]]
+            yy = Ys[m][gsel[g]]
+            ss = float((yy ** 2 * mk).sum())
+            for k in range(K):
+                r2[g, k] = 100.0 * (1.0 - float((((yy - np.outer(Z[gsel[g], k], W[m][:, k])) ** 2) * mk).sum()) / ss)
+        var.append(r2)
+    order = np.arange(K)
+    if sort_factors:
+        order = np.argsort(-np.sum([v.sum(0) for v in var], axis=0), kind="stable")
+    return {"Z": Z[:, order], "W": [w[:, order] for w in W], "variance": [v[:, order] for v in var], "elbo": elbos,
+            "order": order, "iterations": it + 1, "converged": converged, "intercepts": means, "scales": scales}

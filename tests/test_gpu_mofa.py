@@ -7,7 +7,7 @@ import torch
 import muon_b200 as mu
 from muon_b200._containers import SimpleAnnData, SimpleMuData
 from muon_b200._mofa import run_mofa_device
-from oracle.mofa_ref import mofa_ref
+from oracle.mofa_ref import mofa_ref, mofa_ref_general
 
 pytestmark = pytest.mark.gpu
 
@@ -97,3 +97,65 @@ def test_api_semantics(cuda):
         mu.tl.mofa(SimpleMuData({"rna": a, "atac": c}), use_var=None)
     with pytest.raises(NotImplementedError):
         mu.tl.mofa(md, use_var=None, likelihoods="poisson")
+
+
+def test_groups_and_union_match_general_oracle(cuda):
+    """groups_label + use_obs="union" (cells missing from whole views) + scale_groups against the masked,
+    textbook-form float64 oracle -- an independent formulation of the same model."""
+    import pandas as pd
+    N, dims, K = 300, [140, 90], 5
+    views = _planted(N, dims, 3, seed=11)
+    names = [f"c{i}" for i in range(N)]
+    a = SimpleAnnData(views[0][:270], obs=names[:270])
+    b = SimpleAnnData(views[1][30:], obs=names[30:])
+    md = SimpleMuData({"rna": a, "atac": b})
+    assert list(md.obs_names) == names
+    groups = np.array(["g1"] * 120 + ["g2"] * 180)
+    md.obs["grp"] = groups
+    with pytest.raises(IndexError):
+        mu.tl.mofa(md, use_var=None, n_factors=K)
+    for kw in ({}, {"scale_groups": True}):
+        mu.tl.mofa(md, use_var=None, n_factors=K, n_iterations=20, convergence_mode="slow", use_obs="union",
+                   groups_label="grp", seed=3, **kw)
+        Y1 = np.full((N, dims[0]), np.nan)
+        Y1[:270] = views[0][:270].toarray()
+        Y2 = np.full((N, dims[1]), np.nan)
+        Y2[30:] = views[1][30:].toarray()
+        ref = mofa_ref_general([Y1, Y2], groups=groups, n_factors=K, n_iterations=20, convergence_mode="slow",
+                               seed=3, **kw)
+        np.testing.assert_allclose(md.uns["mofa"]["_b200"]["elbo"], ref["elbo"], rtol=1e-5)
+        Zg, Zr = md.obsm["X_mofa"], ref["Z"]
+        act = np.sum([v.sum(0) for v in ref["variance"]], axis=0) > 2.0
+        assert act.sum() >= 2
+        assert (np.abs(Zg - Zr).max(0) / np.abs(Zr).max(0))[act].max() < 2e-4
+        Wr = np.concatenate(ref["W"], axis=0)
+        assert (np.abs(md.varm["LFs"] - Wr).max(0) / np.abs(Wr).max(0))[act].max() < 2e-4
+        assert set(md.uns["mofa"]["variance"]["rna"]) == {"g1", "g2"}
+        np.testing.assert_allclose(md.uns["mofa"]["variance"]["atac"]["g2"][act], ref["variance"][1][1][act], rtol=2e-3)
+
+
+def test_reference_union_and_groups_api(cuda):
+    # reference tests/test_muon_tools.py:56-87 (categorical groups on AnnData; obs union with dense/sparse mixes)
+    import pandas as pd
+    np.random.seed(1000)
+    z = np.random.normal(size=(100, 5))
+    y1 = z @ np.random.normal(size=(90, 5)).T + np.random.normal(size=(100, 90))
+    y2 = z @ np.random.normal(size=(50, 5)).T + np.random.normal(size=(100, 50))
+    ad = SimpleAnnData(y1.copy())
+    ad.obs["ab"] = pd.Categorical(np.random.choice(["a", "b"], 100))
+    with pytest.warns(UserWarning):
+        mu.tl.mofa(ad, groups_label="ab", n_factors=10, quiet=True)
+    assert ad.obsm["X_mofa"].shape == (100, 10) and ad.varm["LFs"].shape == (90, 10)
+    assert np.all(np.isfinite(ad.obsm["X_mofa"]))
+    for sparsity in (0, 1, 2):
+        x1 = sp.csr_matrix(y1) if sparsity in (0, 2) else y1
+        x2 = sp.csr_matrix(y2) if sparsity in (1, 2) else y2
+        A1, A2 = SimpleAnnData(x1), SimpleAnnData(x2)
+        md = SimpleMuData({"y1": A1[:-10], "y2": A2[10:]})
+        with pytest.warns(UserWarning):
+            mu.tl.mofa(md, n_factors=10, quiet=True, use_obs="union")
+        assert md.obsm["X_mofa"].shape == (100, 10) and md.varm["LFs"].shape == (140, 10)
+        md2 = SimpleMuData({"y1": A1[:-10], "y2": A2[10:]})
+        with pytest.warns(UserWarning):
+            mu.tl.mofa(md2, n_factors=10, quiet=True, use_obs="intersection")
+        assert np.isnan(md2.obsm["X_mofa"][:10]).all() and np.isfinite(md2.obsm["X_mofa"][10:90]).all()
