@@ -289,7 +289,7 @@ class TransposedPanels:
     panels whose slice of Y fits in L2 and the products are accumulated panel by panel."""
 
     # bytes of the gathered operand per panel (B200 L2: 126 MB, shared with the CSR stream)
-    L2_BUDGET = int(os.environ.get("MUON_B200_L2_BUDGET_MB", "64")) << 20
+    L2_BUDGET = int(os.environ.get("MUON_B200_L2_BUDGET_MB", "32")) << 20
 
     def __init__(self, A: DeviceCSR, pad: int = 64):
         n = A.shape[0]

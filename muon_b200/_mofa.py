@@ -160,14 +160,13 @@ class MofaDevice:
         self.Ng = torch.tensor([float(x) for x in n_groups_total], dtype=f64, device=dev)
         self.N = int(sum(n_groups_total))
         self.C = self.G << self.M
-        self.cls = cls
         # how many cells of class c each (view, group) block / each group holds (global): for sums of Var[z]
-        counts = torch.zeros(self.C, dtype=f64, device=dev)
-        if cls is None:
+        if cls is None:                                   # every cell observed in every view
+            cls = torch.empty(self.n_local, dtype=torch.int32, device=dev)
             for g, (lo, hi) in enumerate(group_ranges):
-                counts[(g << self.M) | ((1 << self.M) - 1)] = hi - lo
-        else:
-            counts += torch.bincount(cls.to(torch.int64), minlength=self.C).to(f64)
+                cls[lo:hi] = (g << self.M) | ((1 << self.M) - 1)
+        self.cls = cls
+        counts = torch.bincount(cls.to(torch.int64), minlength=self.C).to(f64)
         self.class_count = _dist.all_reduce_sum_(counts)
         self.views = []
         for m in range(self.M):
