@@ -217,10 +217,10 @@ class DeviceCSR:
             self._t = csr_transpose(self)
         return self._t
 
-    def transpose_panels(self, pad: int = 64) -> "TransposedPanels":
+    def transpose_panels(self, pad: int = 64, side_stream: bool = False) -> "TransposedPanels":
         key = ("panels", pad)
         if getattr(self, "_tp", None) is None or self._tp[0] != key:
-            self._tp = (key, TransposedPanels(self, pad))
+            self._tp = (key, TransposedPanels(self, pad, side_stream))
         return self._tp[1]
 
 
@@ -256,19 +256,22 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
     return res
 
 
-def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None) -> DeviceCSR:
+def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None, k0: Optional[int] = None,
+                  k1: Optional[int] = None) -> DeviceCSR:
     """Build the CSR of (A[row0:row1])^T on the device (count -> scan -> atomic-cursor fill).
-    Row indices stored in the result are local to the panel (0 .. row1-row0)."""
+    Row indices stored in the result are local to the panel (0 .. row1-row0).  ``k0``/``k1`` are the
+    non-zero offsets of the row range if the caller already knows them (avoids a host sync)."""
     require_cuda()
     assert A.data.dtype == torch.float32, "transpose: float32 values only"
     n, d = A.shape
     row1 = n if row1 is None else row1
     dev = A.data.device
     st = stream_ptr()
-    if row0 == 0 and row1 == n:
-        k0, k1 = 0, A.nnz
-    else:
-        k0, k1 = int(A.indptr[row0]), int(A.indptr[row1])
+    if k0 is None or k1 is None:
+        if row0 == 0 and row1 == n:
+            k0, k1 = 0, A.nnz
+        else:
+            k0, k1 = int(A.indptr[row0]), int(A.indptr[row1])
     nnz = k1 - k0
     t_count = torch.zeros(d + 1, dtype=torch.int64, device=dev)
     call("mub_csr_transpose_count", ptr(A.indices) + 4 * k0, nnz, d, ptr(t_count), st)
@@ -291,16 +294,39 @@ class TransposedPanels:
     # bytes of the gathered operand per panel (B200 L2: 126 MB, shared with the CSR stream)
     L2_BUDGET = int(os.environ.get("MUON_B200_L2_BUDGET_MB", "32")) << 20
 
-    def __init__(self, A: DeviceCSR, pad: int = 64):
+    def __init__(self, A: DeviceCSR, pad: int = 64, side_stream: bool = False):
         n = A.shape[0]
         rows = max(1, self.L2_BUDGET // (4 * pad))
         n_panels = max(1, -(-n // rows))
         bounds = [round(i * n / n_panels) for i in range(n_panels + 1)]
         self.shape = (A.shape[1], n)
-        self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1]))
-                       for i in range(n_panels)]
+        # non-zero offsets of the panel boundaries: one small D2H up front, no host syncs afterwards
+        ks = A.indptr[torch.tensor(bounds, device=A.indptr.device)].tolist()
+        self.ready = None
+        if side_stream:
+            # build on a second stream so that the first A*V product (main stream) overlaps it;
+            # consumers call wait() before touching the panels
+            main = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1]))
+                               for i in range(n_panels)]
+                self.ready = side.record_event()
+            for _, _, T in self.panels:           # memory is consumed on the main stream later on
+                for t in (T.indptr, T.indices, T.data):
+                    t.record_stream(main)
+        else:
+            self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1]))
+                           for i in range(n_panels)]
+
+    def wait(self):
+        if self.ready is not None:
+            torch.cuda.current_stream().wait_event(self.ready)
+            self.ready = None
 
     def spmm(self, Y: torch.Tensor, dynamic=True) -> torch.Tensor:
+        self.wait()
         out = None
         for r0, r1, T in self.panels:
             if out is None:

@@ -62,6 +62,7 @@ class _View:
             cnt[g] = b.n_local
             if b.n_local == 0:
                 continue
+            b.At.wait()
             for (_, _, T) in b.At.panels:
                 t1, t2 = torch.empty(D, dtype=f64, device=dev), torch.empty(D, dtype=f64, device=dev)
                 call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
