@@ -59,7 +59,7 @@ class CsrOperator:
         self._dev = _device
         self.A = A
         with phase("lsi.transpose"):
-            self.At = A.transpose_panels(pad, side_stream=os.environ.get("MUON_B200_OVERLAP", "1") == "1")
+            self.At = A.transpose_panels(pad, side_stream=os.environ.get("MUON_B200_OVERLAP", "0") == "1")
         self.n_local, self.d = A.shape
         self.n_total = A.n_total
         self.device = A.data.device
