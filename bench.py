@@ -186,8 +186,12 @@ def main():
     nnz = A.nnz
     torch.cuda.synchronize()
 
+    import pandas as pd
+    obs0 = pd.DataFrame(index=pd.RangeIndex(n_local).astype(str))
+    var0 = pd.DataFrame(index=pd.RangeIndex(D).astype(str))
+
     def step():
-        ad = mu.SimpleAnnData(A)                      # counts stay untouched: tfidf writes a new matrix
+        ad = mu.SimpleAnnData(A, obs=obs0, var=var0)  # counts stay untouched: tfidf writes a new matrix
         mu.atac.pp.tfidf(ad)
         info = mu.atac.tl.lsi(ad, n_comps=k, tol=args.tol, return_info=True)
         return ad, info
@@ -273,8 +277,12 @@ def main():
         if Ae is not A:
             del Ae
 
+        import pandas as pd
+        obs_df = pd.DataFrame(index=pd.RangeIndex(ne).astype(str))
+        var_df = pd.DataFrame(index=pd.RangeIndex(D).astype(str))
+
         def step_host():
-            ad = mu.SimpleAnnData(sp.csr_matrix((X.data, X.indices, X.indptr), shape=X.shape, copy=False))
+            ad = mu.SimpleAnnData(X, obs=obs_df, var=var_df)   # tfidf rebinds ad.X; X itself is never modified
             mu.atac.pp.tfidf(ad)
             mu.atac.tl.lsi(ad, n_comps=k, tol=args.tol)
             return float(ad.uns["lsi"]["stdev"][0])

@@ -205,9 +205,17 @@ class DeviceCSR:
         data = to_host(self.data)
         indptr = to_host(self.indptr) if indptr_host is None else indptr_host
         indices = to_host(self.indices) if indices_host is None else indices_host
-        if self.nnz < 2**31 - 1 and indptr.dtype != np.int32:
-            indptr = indptr.astype(np.int32)
-        m = sp.csr_matrix((data, indices, indptr), shape=self.shape, copy=False)
+        # scipy's (data, indices, indptr) constructor scans the index arrays (min/max to pick an index
+        # dtype): ~30 s for 6e9 int64 indices.  The arrays are known-good, so attach them to an empty matrix.
+        if indices.dtype != indptr.dtype:
+            if self.nnz < 2**31 - 1 and max(self.shape) < 2**31 - 1:
+                indptr = indptr.astype(np.int32) if indptr.dtype != np.int32 else indptr
+                indices = indices.astype(np.int32) if indices.dtype != np.int32 else indices
+            else:
+                indices = indices.astype(np.int64) if indices.dtype != np.int64 else indices
+                indptr = indptr.astype(np.int64) if indptr.dtype != np.int64 else indptr
+        m = sp.csr_matrix(self.shape, dtype=data.dtype)
+        m.data, m.indices, m.indptr = data, indices, indptr
         m.has_sorted_indices = bool(self.sorted_indices)
         return m
 
