@@ -38,6 +38,7 @@ typedef void* mub_stream_t; /* cudaStream_t */
 #define MUB_TFIDF_LOG_IDF 2u   /* log_idf=True     preproc.py:107-108 */
 #define MUB_TFIDF_LOG_TFIDF 4u /* log_tfidf=True   preproc.py:116-117 */
 #define MUB_TFIDF_NO_SCALE 8u  /* scale_factor in {None,0,1}: multiply skipped, preproc.py:101 */
+#define MUB_TFIDF_BINARIZE 16u /* treat every stored non-zero as 1: binarize() (preproc.py:132-152) fused in */
 
 int mub_version(void);
 const char* mub_last_error(void);
@@ -53,10 +54,10 @@ int mub_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
  * the reference's output pattern (scipy's matmul merges duplicates and drops zeros). */
 int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const float* data,
                          int64_t n_rows, int32_t n_cols, float* row_sum, float* col_sum,
-                         int32_t* status, mub_stream_t stream);
+                         int32_t* status, uint32_t flags, mub_stream_t stream);
 int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const double* data,
                          int64_t n_rows, int32_t n_cols, double* row_sum, double* col_sum,
-                         int32_t* status, mub_stream_t stream);
+                         int32_t* status, uint32_t flags, mub_stream_t stream);
 /* idf[j] = n_obs_total / col_sum[j], log1p if MUB_TFIDF_LOG_IDF (preproc.py:106-108) */
 int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags,
                       float* idf, mub_stream_t stream);

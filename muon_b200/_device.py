@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _dist
-from ._lib import (TFIDF_LOG_IDF, TFIDF_LOG_TF, TFIDF_LOG_TFIDF, TFIDF_NO_SCALE, MuonB200Error, call, load, ptr,
+from ._lib import (TFIDF_BINARIZE, TFIDF_LOG_IDF, TFIDF_LOG_TF, TFIDF_LOG_TFIDF, TFIDF_NO_SCALE, MuonB200Error, call, load, ptr,
                    stream_ptr)
 
 PAD_WIDTHS = (32, 64, 128)
@@ -234,7 +234,7 @@ class DeviceCSR:
 
 # ------------------------------------------------------------------------------------------
 def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=1e4,
-              inplace_values=False, check_canonical=False) -> Optional[DeviceCSR]:
+              inplace_values=False, check_canonical=False, binarize=False) -> Optional[DeviceCSR]:
     """K1: two fused passes (reduce, apply).  Column sums are allreduced across cell shards
     (muon/_atac/preproc.py:92-119; multi-GPU plan SURVEY section 8e)."""
     require_cuda()
@@ -244,13 +244,15 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
     if scale_factor is None or scale_factor == 0 or scale_factor == 1:
         flags |= TFIDF_NO_SCALE
         scale_factor = 1.0
+    if binarize:
+        flags |= TFIDF_BINARIZE
     dev, dt = A.data.device, A.data.dtype
     row_sum = torch.empty(n, dtype=dt, device=dev)
     col_sum = torch.zeros(d, dtype=dt, device=dev)
     st = stream_ptr()
     status = torch.zeros(1, dtype=torch.int32, device=dev) if check_canonical else None
     call(f"mub_tfidf_reduce_{sfx}", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(row_sum), ptr(col_sum),
-         ptr(status), st)
+         ptr(status), flags, st)
     if check_canonical and int(status[0]) != 0:
         return None  # caller canonicalises (duplicates / explicit zeros / unsorted rows) and retries
     _dist.all_reduce_sum_(col_sum)

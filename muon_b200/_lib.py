@@ -24,8 +24,8 @@ i64, i32, u32, u64, f32, f64, vp = C.c_int64, C.c_int32, C.c_uint32, C.c_uint64,
 SIGNATURES = {
     "mub_version": [],
     "mub_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)],
-    "mub_tfidf_reduce_f32": [vp, vp, vp, i64, i32, vp, vp, vp, vp],
-    "mub_tfidf_reduce_f64": [vp, vp, vp, i64, i32, vp, vp, vp, vp],
+    "mub_tfidf_reduce_f32": [vp, vp, vp, i64, i32, vp, vp, vp, u32, vp],
+    "mub_tfidf_reduce_f64": [vp, vp, vp, i64, i32, vp, vp, vp, u32, vp],
     "mub_tfidf_idf_f32": [vp, i32, f64, u32, vp, vp],
     "mub_tfidf_idf_f64": [vp, i32, f64, u32, vp, vp],
     "mub_tfidf_apply_f32": [vp, vp, vp, vp, i64, i32, vp, vp, f32, u32, vp],
@@ -47,7 +47,7 @@ SPECIAL_RESTYPE = {
     "mub_gram_workspace_bytes": ([i64, i32], C.c_size_t),
 }
 
-TFIDF_LOG_TF, TFIDF_LOG_IDF, TFIDF_LOG_TFIDF, TFIDF_NO_SCALE = 1, 2, 4, 8
+TFIDF_LOG_TF, TFIDF_LOG_IDF, TFIDF_LOG_TFIDF, TFIDF_NO_SCALE, TFIDF_BINARIZE = 1, 2, 4, 8, 16
 
 
 class MuonB200Error(RuntimeError):

@@ -97,3 +97,30 @@ def tfidf(
         adata.X = res
     if copy:
         return adata
+
+
+def binarize(data):
+    """Transform peak counts to the binary matrix (all the non-zero values become 1) -- drop-in for
+    ``muon.atac.pp.binarize`` (reference muon/_atac/preproc.py:132-152): a true in-place write of ``X``.
+
+    Host matrices are edited with numpy exactly like the reference; a device-resident
+    :class:`muon_b200.DeviceCSR` is edited in HBM.  ``tfidf`` on binarized counts can also be done in one
+    fused pass on the device with ``muon_b200._device.tfidf_csr(A, binarize=True)`` (MUB_TFIDF_BINARIZE)."""
+    from .. import _device
+    if is_anndata(data):
+        adata = data
+    elif is_mudata(data) and "atac" in data.mod:
+        adata = data.mod["atac"]
+    else:
+        raise TypeError("Expected AnnData or MuData object with 'atac' modality")
+    X = adata.X
+    if isinstance(X, _device.DeviceCSR):
+        X.data.copy_((X.data != 0).to(X.data.dtype))
+        X._t = None
+        X._tp = None
+        return
+    import scipy.sparse as sp
+    if sp.issparse(X):
+        X.data[X.data != 0] = 1
+    else:
+        X[X != 0] = 1

@@ -23,7 +23,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                     const T* __restrict__ data, int64_t n_rows, T* __restrict__ row_sum,
-                    T* __restrict__ col_sum, int* __restrict__ status) {
+                    T* __restrict__ col_sum, int* __restrict__ status, int binarize) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
@@ -41,6 +41,11 @@ tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
             int c2 = ld_stream(indices + k + 64), c3 = ld_stream(indices + k + 96);
             T v0 = ld_stream(data + k), v1 = ld_stream(data + k + 32);
             T v2 = ld_stream(data + k + 64), v3 = ld_stream(data + k + 96);
+            bad |= ((v0 == T(0)) | (v1 == T(0)) | (v2 == T(0)) | (v3 == T(0))) << 1;
+            if (binarize) {
+                v0 = v0 != T(0) ? T(1) : T(0); v1 = v1 != T(0) ? T(1) : T(0);
+                v2 = v2 != T(0) ? T(1) : T(0); v3 = v3 != T(0) ? T(1) : T(0);
+            }
             atomicAdd(col_sum + c0, v0);
             atomicAdd(col_sum + c1, v1);
             atomicAdd(col_sum + c2, v2);
@@ -54,13 +59,14 @@ tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
             if (lane == 0) { p0 = carry; p1 = l0; p2 = l1; p3 = l2; }
             carry = l3;
             bad |= (c0 <= p0) | (c1 <= p1) | (c2 <= p2) | (c3 <= p3);
-            bad |= ((v0 == T(0)) | (v1 == T(0)) | (v2 == T(0)) | (v3 == T(0))) << 1;
         }
         for (; kb < end; kb += 32) {
             const int64_t k = kb + lane;
             const bool ok = k < end;
             int c = ok ? ld_stream(indices + k) : 0x7fffffff;
             T v = ok ? ld_stream(data + k) : T(1);
+            const bool zero = ok && v == T(0);
+            if (binarize) v = v != T(0) ? T(1) : T(0);
             if (ok) {
                 atomicAdd(col_sum + c, v);
                 acc += v;
@@ -69,7 +75,7 @@ tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
             const int last = __shfl_sync(0xffffffffu, c, 31);
             if (lane == 0) p = carry;
             carry = last;
-            bad |= (ok && c <= p) | ((ok && v == T(0)) << 1);
+            bad |= (ok && c <= p) | (zero << 1);
         }
         acc = warp_sum(acc);
         if (lane == 0) row_sum[row] = acc;
@@ -90,6 +96,7 @@ __global__ void tfidf_idf_kernel(const T* __restrict__ col_sum, int32_t n_cols, 
 template <typename T>
 __device__ __forceinline__ T tfidf_value(T c, T inv_r, T idf, T sf, uint32_t flags) {
     // association order of the reference: ((1/r) * c) * sf -> log1p -> * idf -> log1p
+    if (flags & MUB_TFIDF_BINARIZE) c = (c != T(0)) ? T(1) : T(0);   // binarize() fused (preproc.py:149)
     T t;
     if constexpr (sizeof(T) == 4) {
         t = __fmul_rn(inv_r, c);
@@ -150,12 +157,12 @@ static int grid_for_rows(int64_t n_rows) {
 
 template <typename T>
 int tfidf_reduce(const int64_t* indptr, const int32_t* indices, const T* data, int64_t n_rows,
-                 int32_t n_cols, T* row_sum, T* col_sum, int* status, mub_stream_t stream) {
+                 int32_t n_cols, T* row_sum, T* col_sum, int* status, uint32_t flags, mub_stream_t stream) {
     MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_reduce: negative shape");
     if (n_rows == 0) return 0;
     MUB_REQUIRE(indptr && row_sum && col_sum, "tfidf_reduce: null pointer");
     tfidf_reduce_kernel<T><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
-        indptr, indices, data, n_rows, row_sum, col_sum, status);
+        indptr, indices, data, n_rows, row_sum, col_sum, status, (flags & MUB_TFIDF_BINARIZE) ? 1 : 0);
     return check_launch("tfidf_reduce");
 }
 
@@ -186,14 +193,14 @@ int tfidf_apply(const int64_t* indptr, const int32_t* indices, const T* data_in,
 extern "C" {
 
 int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
-                         int32_t n_cols, float* row_sum, float* col_sum, int32_t* status,
+                         int32_t n_cols, float* row_sum, float* col_sum, int32_t* status, uint32_t flags,
                          mub_stream_t stream) {
-    return mub::tfidf_reduce<float>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, stream);
+    return mub::tfidf_reduce<float>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, flags, stream);
 }
 int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const double* data, int64_t n_rows,
-                         int32_t n_cols, double* row_sum, double* col_sum, int32_t* status,
+                         int32_t n_cols, double* row_sum, double* col_sum, int32_t* status, uint32_t flags,
                          mub_stream_t stream) {
-    return mub::tfidf_reduce<double>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, stream);
+    return mub::tfidf_reduce<double>(indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, flags, stream);
 }
 int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags, float* idf,
                       mub_stream_t stream) {

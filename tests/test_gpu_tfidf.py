@@ -176,3 +176,20 @@ def test_canonical_input_never_takes_the_host_fallback(cuda, monkeypatch):
     got = mu.atac.pp.tfidf(SimpleAnnData(Xu), inplace=False)
     assert calls
     _assert_parity(got, tfidf_ref(X), RTOL32)
+
+
+def test_binarize_and_fused_binarized_tfidf(cuda):
+    from muon_b200 import _device
+    X = generate_host(600, 800, 0.05, n_topics=5, seed=6)
+    ad = SimpleAnnData(X.copy())
+    mu.atac.pp.binarize(ad)                               # reference preproc.py:149: in-place on the host buffer
+    assert set(np.unique(ad.X.data)) == {1.0}
+    ref = tfidf_ref(ad.X)
+    dev = mu.DeviceCSR.from_scipy(X)
+    fused = _device.tfidf_csr(dev, binarize=True).get()    # one fused pass on raw counts
+    _assert_parity(fused, ref, RTOL32)
+    d2 = SimpleAnnData(mu.DeviceCSR.from_scipy(X))
+    mu.atac.pp.binarize(d2)
+    assert float(d2.X.data.min()) == 1.0 and float(d2.X.data.max()) == 1.0
+    with pytest.raises(TypeError):
+        mu.atac.pp.binarize(X)
