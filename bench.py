@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--tol", type=float, default=1e-5)
     ap.add_argument("--sample-cells", type=int, default=2000, help="rows of the CPU-baseline sample")
-    ap.add_argument("--e2e-cells", type=int, default=-1, help="cells per GPU for the e2e leg (-1: same as --cells)")
+    ap.add_argument("--e2e-cells", type=int, default=-1,
+                    help="cells per GPU for the e2e leg (-1: same as --cells at 1 GPU; 250k per GPU under torchrun, "
+                         "where N ranks share one host's PCIe switches, memory bandwidth and RAM)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -269,7 +271,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         import scipy.sparse as sp
-        ne = n_local if args.e2e_cells < 0 else min(args.e2e_cells, n_local)
+        ne = (n_local if world == 1 else min(n_local, 250_000)) if args.e2e_cells < 0 else min(args.e2e_cells, n_local)
         Ae = A if ne == n_local else generate_device(ne, D, args.density, tables=tb, row0=rank * ne, n_total=ne * world)
         X = Ae.get()                                    # host scipy CSR (int64 indices when nnz >= 2^31)
         h2d = X.indptr.nbytes + X.indices.nbytes + X.data.nbytes
