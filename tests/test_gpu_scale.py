@@ -37,7 +37,8 @@ def test_tfidf_properties_beyond_2_31(big):
     aux = X._aux
     # pattern untouched, counts untouched, sums exact (integer-valued fp32 counts)
     assert X.indices.data_ptr() == big.indices.data_ptr() and X.data.data_ptr() != big.data.data_ptr()
-    assert float(aux["col_sum"].sum()) == float(aux["row_sum"].sum()) == float(big.data.sum(dtype=torch.float64))
+    f64 = torch.float64      # each individual sum is an integer < 2^24, exact in fp32; totals need fp64
+    assert float(aux["col_sum"].sum(dtype=f64)) == float(aux["row_sum"].sum(dtype=f64)) == float(big.data.sum(dtype=f64))
     # rows past the 2^31-th non-zero: values equal the closed form evaluated with torch on a re-based slice
     r0 = N - 2000
     S = _slice_rows(big, r0, N)
