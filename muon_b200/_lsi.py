@@ -217,10 +217,17 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
                     Sj = _dist.broadcast_(Sj.contiguous())
             # ---- Rayleigh-Ritz on the block-bidiagonal B (fp64, tiny) ---------------------
             with phase("lsi.ritz_svd"):
-                X, sig, Zt = torch.linalg.svd(Bmat[:m, :m])
-            kk = min(k, m)
+                # Ritz triplets of the block-bidiagonal B through eigh(B^T B) in fp64 (several times cheaper
+                # than a full SVD; the squared condition number is harmless at 1e-16).  Only the last block
+                # row of the left vectors is needed for the residuals: X = B Z / sigma.
+                Bm = Bmat[:m, :m]
+                lam, Zr = torch.linalg.eigh(Bm.T @ Bm)
+                kk = min(k, m)
+                sig = lam.flip(0).clamp_min(0).sqrt()
+                Zt = Zr.flip(1).T.contiguous()
+                Xlast = (Bm[j0:j1, :] @ Zt[:kk, :].T) / sig[:kk].clamp_min(1e-300)
             if Sj is not None:
-                res = torch.linalg.norm(Sj @ X[j0:j1, :kk], dim=0) / sig[:kk].clamp_min(1e-300)
+                res = torch.linalg.norm(Sj @ Xlast, dim=0) / sig[:kk].clamp_min(1e-300)
             else:
                 res = torch.zeros(kk, dtype=f64, device=dev)
             if _dist.is_distributed():                   # one rank decides: control flow must not diverge
