@@ -64,14 +64,12 @@ int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, 
 int mub_tfidf_idf_f64(const double* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags,
                       double* idf, mub_stream_t stream);
 /* pass 2: out_ij = log1p(((1/r_i) * c_ij) * sf) * idf_j   (preproc.py:94-96,101-104,110-112,
- * 116-117), association order as written.  data_out may alias data_in (in place).  nnz = indptr[n_rows]
- * if the caller knows it (enables the flat 16-byte-vectorised form when the arrays are 16-byte aligned),
- * or -1 (row-warp form). */
+ * 116-117), association order as written.  data_out may alias data_in (in place). */
 int mub_tfidf_apply_f32(const int64_t* indptr, const int32_t* indices, const float* data_in,
-                        float* data_out, int64_t n_rows, int32_t n_cols, int64_t nnz, const float* row_sum,
+                        float* data_out, int64_t n_rows, int32_t n_cols, const float* row_sum,
                         const float* idf, float scale_factor, uint32_t flags, mub_stream_t stream);
 int mub_tfidf_apply_f64(const int64_t* indptr, const int32_t* indices, const double* data_in,
-                        double* data_out, int64_t n_rows, int32_t n_cols, int64_t nnz, const double* row_sum,
+                        double* data_out, int64_t n_rows, int32_t n_cols, const double* row_sum,
                         const double* idf, double scale_factor, uint32_t flags, mub_stream_t stream);
 
 /* ---- CSR x dense SpMM: the operator applications inside svds ------------------------------

@@ -259,7 +259,7 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
     idf = torch.empty(d, dtype=dt, device=dev)
     call(f"mub_tfidf_idf_{sfx}", ptr(col_sum), d, float(A.n_total), flags, ptr(idf), st)
     out = A.data if inplace_values else torch.empty_like(A.data)
-    call(f"mub_tfidf_apply_{sfx}", ptr(A.indptr), ptr(A.indices), ptr(A.data), ptr(out), n, d, A.nnz, ptr(row_sum),
+    call(f"mub_tfidf_apply_{sfx}", ptr(A.indptr), ptr(A.indices), ptr(A.data), ptr(out), n, d, ptr(row_sum),
          ptr(idf), float(scale_factor), flags, st)
     res = A.with_data(out)
     res._aux = {"row_sum": row_sum, "col_sum": col_sum, "idf": idf}

@@ -28,8 +28,8 @@ SIGNATURES = {
     "mub_tfidf_reduce_f64": [vp, vp, vp, i64, i32, vp, vp, vp, u32, vp],
     "mub_tfidf_idf_f32": [vp, i32, f64, u32, vp, vp],
     "mub_tfidf_idf_f64": [vp, i32, f64, u32, vp, vp],
-    "mub_tfidf_apply_f32": [vp, vp, vp, vp, i64, i32, i64, vp, vp, f32, u32, vp],
-    "mub_tfidf_apply_f64": [vp, vp, vp, vp, i64, i32, i64, vp, vp, f64, u32, vp],
+    "mub_tfidf_apply_f32": [vp, vp, vp, vp, i64, i32, vp, vp, f32, u32, vp],
+    "mub_tfidf_apply_f64": [vp, vp, vp, vp, i64, i32, vp, vp, f64, u32, vp],
     "mub_spmm_csr_f32": [vp, vp, vp, i64, i64, vp, i32, vp, i32, vp, vp],
     "mub_spmm_csr_panel_f32": [vp, vp, vp, i64, i64, vp, i32, vp, i32, vp],
     "mub_csr_transpose_count": [vp, i64, i32, vp, vp],

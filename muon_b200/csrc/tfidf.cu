@@ -19,11 +19,11 @@ namespace mub {
 constexpr int kThreads = 256;
 constexpr int kWarpsPerCta = kThreads / kWarp;
 
-template <typename T>
+template <typename T, bool binarize>
 __global__ void __launch_bounds__(kThreads)
 tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                     const T* __restrict__ data, int64_t n_rows, T* __restrict__ row_sum,
-                    T* __restrict__ col_sum, int* __restrict__ status, int binarize) {
+                    T* __restrict__ col_sum, int* __restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
@@ -147,100 +147,6 @@ tfidf_apply_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict
     }
 }
 
-// Flat variant of pass 2: the nnz axis is cut into 4096-element chunks (one warp each, round-robin so that
-// consecutive warps stream consecutive memory); every lane moves 16 bytes of indices and 16 bytes of
-// values per load (int4 / float4, or int2 / double2) and tracks the row of its elements with a cursor
-// that starts from a binary search in indptr.  4x fewer load/store instructions than the row-warp form
-// and perfect load balance for any row-length distribution.
-template <typename T>
-struct ApplyVec;
-template <>
-struct ApplyVec<float> {
-    static constexpr int N = 4;
-    using V = float4;
-    using I = int4;
-};
-template <>
-struct ApplyVec<double> {
-    static constexpr int N = 2;
-    using V = double2;
-    using I = int2;
-};
-
-__device__ __forceinline__ int2 ld_stream2(const int2* p) {
-    int2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-tfidf_apply_flat_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const T* data_in,
-                        T* data_out, int64_t n_rows, int64_t nnz, const T* __restrict__ row_sum,
-                        const T* __restrict__ idf, T sf, uint32_t flags) {
-    constexpr int N = ApplyVec<T>::N;
-    constexpr int64_t CH = 4096;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
-    const int64_t n_chunks = (nnz + CH - 1) / CH;
-    for (int64_t ch = warp; ch < n_chunks; ch += n_warps) {
-        const int64_t k0 = ch * CH, k1 = (k0 + CH < nnz) ? k0 + CH : nnz;
-        int64_t k = k0 + (int64_t)lane * N;
-        if (k >= k1) continue;
-        // row of element k: largest r with indptr[r] <= k (upper bound - 1)
-        int64_t lo = 0, hi = n_rows;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (__ldg(indptr + mid + 1) <= k) lo = mid + 1; else hi = mid;
-        }
-        int64_t row = lo;
-        int64_t row_end = __ldg(indptr + row + 1);
-        T inv_r = T(1) / __ldg(row_sum + row);
-        for (; k < k1; k += 32 * N) {
-            T v[N];
-            int c[N];
-            if (k + N <= k1) {
-                if constexpr (N == 4) {
-                    const int4 ci = ld_stream4(reinterpret_cast<const int4*>(indices + k));
-                    const float4 vi = *reinterpret_cast<const float4*>(data_in + k);
-                    c[0] = ci.x; c[1] = ci.y; c[2] = ci.z; c[3] = ci.w;
-                    v[0] = vi.x; v[1] = vi.y; v[2] = vi.z; v[3] = vi.w;
-                } else {
-                    const int2 ci = ld_stream2(reinterpret_cast<const int2*>(indices + k));
-                    const double2 vi = *reinterpret_cast<const double2*>(data_in + k);
-                    c[0] = ci.x; c[1] = ci.y;
-                    v[0] = vi.x; v[1] = vi.y;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < N; ++e) {
-                    c[e] = (k + e < k1) ? ld_stream(indices + k + e) : 0;
-                    v[e] = (k + e < k1) ? ld_stream_rw(data_in + k + e) : T(0);
-                }
-            }
-            T o[N];
-#pragma unroll
-            for (int e = 0; e < N; ++e) {
-                while (k + e >= row_end && row + 1 < n_rows) {
-                    ++row;
-                    row_end = __ldg(indptr + row + 1);
-                    inv_r = T(1) / __ldg(row_sum + row);
-                }
-                o[e] = tfidf_value(v[e], inv_r, __ldg(idf + c[e]), sf, flags);
-            }
-            if (k + N <= k1) {
-                if constexpr (N == 4) *reinterpret_cast<float4*>(data_out + k) = make_float4(o[0], o[1], o[2], o[3]);
-                else *reinterpret_cast<double2*>(data_out + k) = make_double2(o[0], o[1]);
-            } else {
-#pragma unroll
-                for (int e = 0; e < N; ++e)
-                    if (k + e < k1) data_out[k + e] = o[e];
-            }
-        }
-    }
-}
-
 static int grid_for_rows(int64_t n_rows) {
     // persistent-style: 8 CTAs of 256 threads per SM (full occupancy), never more warps than rows
     int64_t want = (n_rows + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -255,8 +161,12 @@ int tfidf_reduce(const int64_t* indptr, const int32_t* indices, const T* data, i
     MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_reduce: negative shape");
     if (n_rows == 0) return 0;
     MUB_REQUIRE(indptr && row_sum && col_sum, "tfidf_reduce: null pointer");
-    tfidf_reduce_kernel<T><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
-        indptr, indices, data, n_rows, row_sum, col_sum, status, (flags & MUB_TFIDF_BINARIZE) ? 1 : 0);
+    if (flags & MUB_TFIDF_BINARIZE)
+        tfidf_reduce_kernel<T, true><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
+            indptr, indices, data, n_rows, row_sum, col_sum, status);
+    else
+        tfidf_reduce_kernel<T, false><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
+            indptr, indices, data, n_rows, row_sum, col_sum, status);
     return check_launch("tfidf_reduce");
 }
 
@@ -271,22 +181,12 @@ int tfidf_idf(const T* col_sum, int32_t n_cols, double n_obs, uint32_t flags, T*
 
 template <typename T>
 int tfidf_apply(const int64_t* indptr, const int32_t* indices, const T* data_in, T* data_out,
-                int64_t n_rows, int32_t n_cols, int64_t nnz, const T* row_sum, const T* idf, T sf, uint32_t flags,
+                int64_t n_rows, int32_t n_cols, const T* row_sum, const T* idf, T sf, uint32_t flags,
                 mub_stream_t stream) {
     MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_apply: negative shape");
     MUB_REQUIRE(!((flags & MUB_TFIDF_LOG_TFIDF) && (flags & (MUB_TFIDF_LOG_TF | MUB_TFIDF_LOG_IDF))),
                 "tfidf_apply: LOG_TFIDF excludes LOG_TF/LOG_IDF (preproc.py:69-73)");
     if (n_rows == 0) return 0;
-    const bool aligned = ((((uintptr_t)indices) | ((uintptr_t)data_in) | ((uintptr_t)data_out)) & 15) == 0;
-    if (aligned && nnz >= 0) {   // flat, vectorised form (needs nnz = indptr[n_rows] from the caller: no sync here)
-        if (nnz == 0) return 0;
-        const int64_t want = ((nnz + 4095) / 4096 + kWarpsPerCta - 1) / kWarpsPerCta;
-        const int64_t cap = (int64_t)sm_count() * 8;
-        const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-        tfidf_apply_flat_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>(indptr, indices, data_in, data_out,
-                                                                              n_rows, nnz, row_sum, idf, sf, flags);
-        return check_launch("tfidf_apply_flat");
-    }
     tfidf_apply_kernel<T><<<grid_for_rows(n_rows), kThreads, 0, (cudaStream_t)stream>>>(
         indptr, indices, data_in, data_out, n_rows, row_sum, idf, sf, flags);
     return check_launch("tfidf_apply");
@@ -315,15 +215,15 @@ int mub_tfidf_idf_f64(const double* col_sum, int32_t n_cols, double n_obs_total,
     return mub::tfidf_idf<double>(col_sum, n_cols, n_obs_total, flags, idf, stream);
 }
 int mub_tfidf_apply_f32(const int64_t* indptr, const int32_t* indices, const float* data_in, float* data_out,
-                        int64_t n_rows, int32_t n_cols, int64_t nnz, const float* row_sum, const float* idf,
+                        int64_t n_rows, int32_t n_cols, const float* row_sum, const float* idf,
                         float scale_factor, uint32_t flags, mub_stream_t stream) {
-    return mub::tfidf_apply<float>(indptr, indices, data_in, data_out, n_rows, n_cols, nnz, row_sum, idf,
+    return mub::tfidf_apply<float>(indptr, indices, data_in, data_out, n_rows, n_cols, row_sum, idf,
                                    scale_factor, flags, stream);
 }
 int mub_tfidf_apply_f64(const int64_t* indptr, const int32_t* indices, const double* data_in,
-                        double* data_out, int64_t n_rows, int32_t n_cols, int64_t nnz, const double* row_sum,
+                        double* data_out, int64_t n_rows, int32_t n_cols, const double* row_sum,
                         const double* idf, double scale_factor, uint32_t flags, mub_stream_t stream) {
-    return mub::tfidf_apply<double>(indptr, indices, data_in, data_out, n_rows, n_cols, nnz, row_sum, idf,
+    return mub::tfidf_apply<double>(indptr, indices, data_in, data_out, n_rows, n_cols, row_sum, idf,
                                     scale_factor, flags, stream);
 }
 
