@@ -9,6 +9,7 @@ Outputs (small, committed):
   tfidf_sparse.npz  the reference test's sparse 100x10 input (:56-59) + output for several flag sets
   tfidf_synth.npz   300x400 synthetic counts (float32) + reference output
   lsi_synth.npz     reference lsi() on the TF-IDF of a 600x500 synthetic matrix, k=8
+  signatures.json   parameter names/defaults of tfidf, binarize, lsi, mofa (ast, no import)
 """
 import os
 import sys
@@ -82,5 +83,31 @@ def main():
             print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+
+
+def dump_signatures():
+    """Parameter names and defaults of the three reference entry points, read with ``ast`` (no import):
+    muon/_atac/preproc.py::tfidf, ::binarize, muon/_atac/tools.py::lsi, muon/_core/tools.py::mofa."""
+    import ast
+    import json
+    from oracle._refload import REF_ROOT
+    out = {}
+    for rel, names in (("muon/_atac/preproc.py", ("tfidf", "binarize")), ("muon/_atac/tools.py", ("lsi",)),
+                       ("muon/_core/tools.py", ("mofa",))):
+        tree = ast.parse(open(os.path.join(REF_ROOT, rel)).read())
+        for node in tree.body:
+            if isinstance(node, ast.FunctionDef) and node.name in names:
+                args = node.args
+                params = [a.arg for a in args.args]
+                defaults = [ast.literal_eval(d) for d in args.defaults]
+                defaults = [None] * (len(params) - len(defaults)) + defaults
+                required = len(params) - len(args.defaults)
+                out[node.name] = {"params": params, "defaults": [repr(d) for d in defaults], "required": required}
+    json.dump(out, open(os.path.join(OUT, "signatures.json"), "w"), indent=1)
+    print("signatures.json", {k: len(v["params"]) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--signatures-only" not in sys.argv:
+        main()
+    dump_signatures()
