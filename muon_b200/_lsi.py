@@ -28,7 +28,6 @@ operator of their own.
 """
 from __future__ import annotations
 
-import math
 import os
 from dataclasses import dataclass, field
 from typing import Optional

@@ -5,7 +5,6 @@ import os
 import socket
 
 import numpy as np
-import pytest
 import scipy.sparse as sp
 import torch
 import torch.distributed as dist

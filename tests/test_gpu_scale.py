@@ -1,7 +1,6 @@
 """GPU, BASELINE-scale shapes: size-independent properties instead of an oracle (the scipy path cannot
 hold these matrices).  400k cells x 200k peaks at 3 % = 2.4e9 non-zeros, i.e. beyond 2^31 so that every
 64-bit offset path is exercised; the full 1M-cell configuration runs in bench.py."""
-import numpy as np
 import pytest
 import torch
 
