@@ -495,6 +495,21 @@ def mofa(
         Xs.append(X)
         masks.append(mask)
 
+    if lik is None:
+        # The reference lets mofapy2 guess the likelihood per view (tools.py:272-280): all values in {0,1} ->
+        # bernoulli, all integers -> poisson, else gaussian.  Those two need dense N x D pseudo-data and are not
+        # implemented here: say so instead of silently fitting a different model.
+        for m, X in zip(mods, Xs):
+            vals = X.data if hasattr(X, "data") and not isinstance(X, np.ndarray) else np.asarray(X).ravel()
+            if isinstance(vals, torch.Tensor):
+                vals = vals[:: max(1, vals.numel() // 1_000_000)].cpu().numpy()
+            else:
+                vals = np.asarray(vals)[:: max(1, vals.size // 1_000_000)]
+            if vals.size and np.all(vals == np.round(vals)):
+                kind = "bernoulli" if np.all((vals == 0) | (vals == 1)) else "poisson"
+                warn(f"view '{m}' holds only integer values: the reference would pick the {kind} likelihood; "
+                     "muon_b200 fits the gaussian model (pass likelihoods='gaussian' to silence this)")
+
     if simple:
         views = [_to_device_view(X) for X in Xs]
         n_local, n_total, row0 = views[0].shape[0], views[0].n_total, views[0].row0
