@@ -72,3 +72,14 @@ def test_lsi_device_resident_pipeline_and_errors(cuda):
     small = SimpleAnnData(sp.random(200, 12, 0.5, format="csr", random_state=0, dtype=np.float32))
     mu.atac.tl.lsi(small, n_comps=5)
     assert small.obsm["X_lsi"].shape == (200, 5)
+
+
+def test_lsi_dense_input_and_mudata(cuda):
+    from muon_b200._containers import SimpleMuData
+    X = tfidf_ref(generate_host(500, 300, 0.1, n_topics=5, seed=2)).astype(np.float64)
+    ref = lsi_ref(X, 6, dtype=np.float64)
+    ad = SimpleAnnData(X.toarray())                       # dense ndarray X, float64 -> float64 slots
+    md = SimpleMuData({"atac": ad, "rna": SimpleAnnData(np.ones((500, 3)))})
+    mu.atac.tl.lsi(md, n_comps=6)
+    assert ad.obsm["X_lsi"].dtype == np.float64 and ad.varm["LSI"].shape == (300, 6)
+    np.testing.assert_allclose(ad.uns["lsi"]["stdev"], ref["stdev"], rtol=1e-5)

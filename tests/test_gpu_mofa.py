@@ -159,3 +159,17 @@ def test_reference_union_and_groups_api(cuda):
         with pytest.warns(UserWarning):
             mu.tl.mofa(md2, n_factors=10, quiet=True, use_obs="intersection")
         assert np.isnan(md2.obsm["X_mofa"][:10]).all() and np.isfinite(md2.obsm["X_mofa"][10:90]).all()
+
+
+def test_device_resident_views_and_layers(cuda):
+    views = _planted(400, [150, 100], 3, seed=5)
+    a = SimpleAnnData(mu.DeviceCSR.from_scipy(views[0]))
+    b = SimpleAnnData(None, layers={"norm": views[1]}, shape=views[1].shape)
+    b.X = views[1] * 0                                     # X is ignored when use_layer is given
+    a.layers["norm"] = a.X
+    md = SimpleMuData({"rna": a, "atac": b})
+    mu.tl.mofa(md, use_var=None, use_layer="norm", n_factors=4, n_iterations=15, likelihoods="gaussian")
+    host = SimpleMuData({"rna": SimpleAnnData(views[0]), "atac": SimpleAnnData(views[1])})
+    mu.tl.mofa(host, use_var=None, n_factors=4, n_iterations=15, likelihoods="gaussian")
+    np.testing.assert_allclose(md.obsm["X_mofa"], host.obsm["X_mofa"], rtol=1e-4, atol=1e-5)
+    assert md.uns["mofa"]["params"]["data"]["use_layer"] == "norm"

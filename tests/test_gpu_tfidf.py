@@ -193,3 +193,14 @@ def test_binarize_and_fused_binarized_tfidf(cuda):
     assert float(d2.X.data.min()) == 1.0 and float(d2.X.data.max()) == 1.0
     with pytest.raises(TypeError):
         mu.atac.pp.binarize(X)
+
+
+@pytest.mark.parametrize("dt", [np.int32, np.uint16, np.int64])
+def test_integer_dtypes_follow_reference_dtype_flow(cuda, dt):
+    # integer counts -> float64 result, values equal to the reference to 1e-12
+    X = generate_host(300, 250, 0.08, n_topics=4, seed=3)
+    Xi = sp.csr_matrix((X.data.astype(dt), X.indices, X.indptr), shape=X.shape)
+    ref = tfidf_ref(Xi)
+    got = mu.atac.pp.tfidf(SimpleAnnData(Xi.copy()), inplace=False)
+    assert got.dtype == np.float64 == ref.dtype
+    _assert_parity(got, ref, RTOL64)
