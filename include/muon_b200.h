@@ -105,6 +105,20 @@ int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const 
                            const int64_t* t_indptr, int64_t* cursor, int32_t* t_indices,
                            float* t_data, mub_stream_t stream);
 
+/* "Pairs" layout for transposed panels: entry k of row j is the 8-byte pair {int32 index, float32 value bits},
+ * so the scatter writes once per non-zero and the product reads one 8-byte word per entry.
+ * fill_pairs: like mub_csr_transpose_fill, writing t_pairs[2*nnz] (int32 view of the int2 array).
+ * spmm_csrp : C (+)= A B for a pairs-layout matrix (same kernel family and rules as mub_spmm_csr_f32).
+ * csrp_row_stats: mub_csr_row_stats_f32 on the pairs layout. */
+int mub_csr_transpose_fill_pairs(const int64_t* indptr, const int32_t* indices, const float* data,
+                                 int64_t n_rows, int32_t n_cols, int64_t row_offset, const int64_t* t_indptr,
+                                 int64_t* cursor, int32_t* t_pairs, mub_stream_t stream);
+int mub_spmm_csrp_f32(const int64_t* indptr, const int32_t* pairs, int64_t n_rows, int64_t n_cols,
+                      const float* B, int32_t ld, float* C, int32_t accumulate, unsigned long long* row_counter,
+                      mub_stream_t stream);
+int mub_csrp_row_stats_f32(const int64_t* indptr, const int32_t* pairs, int64_t n_rows, double* sum,
+                           double* sumsq, mub_stream_t stream);
+
 /* per-row sum and sum of squares of a CSR (fp64).  On the CSR of A^T these are the per-feature
  * moments behind MOFA's centring / intercepts (muon/_core/tools.py:283-287, mofapy2 process_data). */
 int mub_csr_row_stats_f32(const int64_t* indptr, const float* data, int64_t n_rows, double* sum,

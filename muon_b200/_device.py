@@ -232,6 +232,29 @@ class DeviceCSR:
         return self._tp[1]
 
 
+class DevicePairs:
+    """CSR whose entries are interleaved 8-byte {int32 index, float32 value} pairs (``pairs``: int32 [nnz, 2]).
+    Used for the transposed row panels: one scattered store per non-zero when building, one 8-byte load per
+    entry when multiplying."""
+
+    def __init__(self, indptr, pairs, shape):
+        self.indptr, self.pairs = indptr, pairs
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.sorted_indices = False
+
+    @property
+    def nnz(self) -> int:
+        return int(self.pairs.shape[0])
+
+    @property
+    def indices(self):
+        return self.pairs[:, 0]
+
+    @property
+    def data(self):
+        return self.pairs[:, 1].view(torch.float32)
+
+
 # ------------------------------------------------------------------------------------------
 def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=1e4,
               inplace_values=False, check_canonical=False, binarize=False) -> Optional[DeviceCSR]:
@@ -267,7 +290,7 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
 
 
 def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None, k0: Optional[int] = None,
-                  k1: Optional[int] = None) -> DeviceCSR:
+                  k1: Optional[int] = None, pairs: bool = False):
     """Build the CSR of (A[row0:row1])^T on the device (count -> scan -> atomic-cursor fill).
     Row indices stored in the result are local to the panel (0 .. row1-row0).  ``k0``/``k1`` are the
     non-zero offsets of the row range if the caller already knows them (avoids a host sync)."""
@@ -287,6 +310,11 @@ def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None, k0: O
     call("mub_csr_transpose_count", ptr(A.indices) + 4 * k0, nnz, d, ptr(t_count), st)
     t_indptr = torch.cumsum(t_count, 0)
     cursor = torch.empty(max(d, 1), dtype=torch.int64, device=dev)
+    if pairs:
+        t_pairs = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
+        call("mub_csr_transpose_fill_pairs", ptr(A.indptr) + 8 * row0, ptr(A.indices), ptr(A.data), row1 - row0, d, 0,
+             ptr(t_indptr), ptr(cursor), ptr(t_pairs), st)
+        return DevicePairs(t_indptr, t_pairs, (d, row1 - row0))
     t_indices = torch.empty(nnz, dtype=torch.int32, device=dev)
     t_data = torch.empty(nnz, dtype=torch.float32, device=dev)
     # indptr values are absolute offsets into indices/data, so only the indptr pointer is shifted;
@@ -320,14 +348,14 @@ class TransposedPanels:
             side = torch.cuda.Stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1]))
+                self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True))
                                for i in range(n_panels)]
                 self.ready = side.record_event()
             for _, _, T in self.panels:           # memory is consumed on the main stream later on
-                for t in (T.indptr, T.indices, T.data):
+                for t in (T.indptr, T.pairs):
                     t.record_stream(main)
         else:
-            self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1]))
+            self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True))
                            for i in range(n_panels)]
 
     def wait(self):
@@ -358,6 +386,11 @@ def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accu
     if out is None:
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=B.device)
+    if isinstance(A, DevicePairs):
+        counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
+        call("mub_spmm_csrp_f32", ptr(A.indptr), ptr(A.pairs), n, d, ptr(B), P, ptr(out), 1 if accumulate else 0,
+             ptr(counter), stream_ptr())
+        return out
     if algo is None:
         algo = os.environ.get("MUON_B200_SPMM", "auto")
     if algo == "auto":

@@ -36,6 +36,9 @@ SIGNATURES = {
     "mub_csr_transpose_fill": [vp, vp, vp, i64, i32, i64, vp, vp, vp, vp, vp],
     "mub_gram_f32": [vp, vp, i64, i32, i32, vp, vp, vp],
     "mub_csr_row_stats_f32": [vp, vp, i64, vp, vp, vp],
+    "mub_csr_transpose_fill_pairs": [vp, vp, vp, i64, i32, i64, vp, vp, vp, vp],
+    "mub_spmm_csrp_f32": [vp, vp, i64, i64, vp, i32, vp, i32, vp, vp],
+    "mub_csrp_row_stats_f32": [vp, vp, i64, vp, vp, vp],
     "mub_mofa_update_w_f32": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],
     "mub_mofa_update_z_f32": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp],
     "mub_mofa_tau_f32": [vp, vp, vp, f64, vp, vp, vp, vp, f64, vp, i64, i32, i32, vp],
@@ -81,7 +84,7 @@ def load():
 
 
 # kernels launched per successful call (for the benchmark's gpu_launches claim)
-KERNELS_PER_CALL = {"mub_csr_transpose_fill": 2, "mub_gram_f32": 2, "mub_version": 0, "mub_device_info": 0}
+KERNELS_PER_CALL = {"mub_csr_transpose_fill": 2, "mub_csr_transpose_fill_pairs": 2, "mub_gram_f32": 2, "mub_version": 0, "mub_device_info": 0}
 LAUNCHES = 0          # running count of kernels launched through this binding
 PROFILE = None        # None, or dict name -> list[(start_event, end_event)] filled by call()
 

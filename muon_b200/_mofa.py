@@ -65,7 +65,10 @@ class _View:
             b.At.wait()
             for (_, _, T) in b.At.panels:
                 t1, t2 = torch.empty(D, dtype=f64, device=dev), torch.empty(D, dtype=f64, device=dev)
-                call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
+                if isinstance(T, _device.DevicePairs):
+                    call("mub_csrp_row_stats_f32", ptr(T.indptr), ptr(T.pairs), D, ptr(t1), ptr(t2), stream_ptr())
+                else:
+                    call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
                 s1[g] += t1
                 s2[g] += t2
         _dist.all_reduce_sum_(s1)

@@ -68,6 +68,11 @@ __device__ __forceinline__ int4 ld_stream4(const int4* p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ int2 ld_stream2(const int2* p) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float4 ld_stream4(const float4* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -22,7 +22,21 @@ namespace mub {
 constexpr int kSpmmThreads = 256;
 constexpr int kSpmmWarps = kSpmmThreads / kWarp;
 
-template <int P>
+// PAIRS: the matrix stores interleaved (column, value) pairs (int2; transposed panels) instead of two arrays
+template <bool PAIRS>
+__device__ __forceinline__ void load_entry(const int32_t* __restrict__ indices, const float* __restrict__ data,
+                                           int64_t k, int& c, float& v) {
+    if constexpr (PAIRS) {
+        const int2 e = ld_stream2(reinterpret_cast<const int2*>(indices) + k);
+        c = e.x;
+        v = __int_as_float(e.y);
+    } else {
+        c = ld_stream(indices + k);
+        v = ld_stream(data + k);
+    }
+}
+
+template <int P, bool PAIRS>
 __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ indices, const float* __restrict__ data,
                                          int64_t start, int64_t end, const float* __restrict__ B,
                                          float* __restrict__ C_row, int accumulate, int lane) {
@@ -35,8 +49,9 @@ __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ indices, co
     int64_t base = start;
     // full 32-nnz segments: all STEPS gathers issued back to back
     for (; base + 32 <= end; base += 32) {
-        const int c = ld_stream(indices + base + lane);
-        const float v = ld_stream(data + base + lane);
+        int c;
+        float v;
+        load_entry<PAIRS>(indices, data, base + lane, c, v);
         constexpr int BATCH = STEPS < 16 ? STEPS : 16;  // gathers in flight per lane
 #pragma unroll
         for (int t0 = 0; t0 < STEPS; t0 += BATCH) {
@@ -60,8 +75,9 @@ __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ indices, co
     if (base < end) {  // tail segment (warp-uniform trip count)
         const int cnt = (int)(end - base);
         const bool ok = lane < cnt;
-        const int c = ok ? ld_stream(indices + base + lane) : 0;
-        const float v = ok ? ld_stream(data + base + lane) : 0.f;
+        int c = 0;
+        float v = 0.f;
+        if (ok) load_entry<PAIRS>(indices, data, base + lane, c, v);
         const int steps = (cnt + G - 1) / G;
         for (int t = 0; t < steps; ++t) {
             const int src = t * G + grp;
@@ -94,7 +110,7 @@ __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ indices, co
     }
 }
 
-template <int P>
+template <int P, bool PAIRS>
 __global__ void __launch_bounds__(kSpmmThreads)
 spmm_csr_rowwarp_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                         const float* __restrict__ data, int64_t n_rows, const float* __restrict__ B,
@@ -105,7 +121,7 @@ spmm_csr_rowwarp_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
         const int64_t n_warps = (int64_t)gridDim.x * kSpmmWarps;
         for (int64_t row = warp; row < n_rows; row += n_warps) {
             const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
-            spmm_row<P>(indices, data, s, e, B, C + (size_t)row * P, accumulate, lane);
+            spmm_row<P, PAIRS>(indices, data, s, e, B, C + (size_t)row * P, accumulate, lane);
         }
     } else {
         // dynamic scheduling: each warp claims the next unprocessed row (rows are issued in
@@ -116,12 +132,12 @@ spmm_csr_rowwarp_kernel(const int64_t* __restrict__ indptr, const int32_t* __res
             row = __shfl_sync(0xffffffffu, row, 0);
             if ((int64_t)row >= n_rows) break;
             const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
-            spmm_row<P>(indices, data, s, e, B, C + (size_t)row * P, accumulate, lane);
+            spmm_row<P, PAIRS>(indices, data, s, e, B, C + (size_t)row * P, accumulate, lane);
         }
     }
 }
 
-template <int P>
+template <int P, bool PAIRS>
 static int launch_spmm(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
                        const float* B, float* C, int accumulate, unsigned long long* row_counter,
                        cudaStream_t stream) {
@@ -129,7 +145,7 @@ static int launch_spmm(const int64_t* indptr, const int32_t* indices, const floa
     int64_t cap = (int64_t)sm_count() * 8;  // 2048 threads / SM
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    spmm_csr_rowwarp_kernel<P><<<grid, kSpmmThreads, 0, stream>>>(indptr, indices, data, n_rows, B, C,
+    spmm_csr_rowwarp_kernel<P, PAIRS><<<grid, kSpmmThreads, 0, stream>>>(indptr, indices, data, n_rows, B, C,
                                                                    accumulate, row_counter);
     return check_launch("spmm_csr");
 }
@@ -146,8 +162,24 @@ extern "C" int mub_spmm_csr_f32(const int64_t* indptr, const int32_t* indices, c
     MUB_REQUIRE((((uintptr_t)B | (uintptr_t)C) & 15) == 0, "spmm_csr: B and C must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     switch (ld) {
-        case 32: return mub::launch_spmm<32>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
-        case 64: return mub::launch_spmm<64>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
-        default: return mub::launch_spmm<128>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
+        case 32: return mub::launch_spmm<32, false>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
+        case 64: return mub::launch_spmm<64, false>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
+        default: return mub::launch_spmm<128, false>(indptr, indices, data, n_rows, B, C, accumulate, row_counter, s);
+    }
+}
+
+extern "C" int mub_spmm_csrp_f32(const int64_t* indptr, const int32_t* pairs, int64_t n_rows, int64_t n_cols,
+                                 const float* B, int32_t ld, float* C, int32_t accumulate,
+                                 unsigned long long* row_counter, mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "spmm_csrp: negative shape");
+    MUB_REQUIRE(ld == 32 || ld == 64 || ld == 128, "spmm_csrp: ld must be 32, 64 or 128 (got %d)", ld);
+    if (n_rows == 0) return 0;
+    MUB_REQUIRE(indptr && B && C, "spmm_csrp: null pointer");
+    MUB_REQUIRE((((uintptr_t)B | (uintptr_t)C) & 15) == 0 && ((uintptr_t)pairs & 7) == 0, "spmm_csrp: misaligned operand");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (ld) {
+        case 32: return mub::launch_spmm<32, true>(indptr, pairs, nullptr, n_rows, B, C, accumulate, row_counter, s);
+        case 64: return mub::launch_spmm<64, true>(indptr, pairs, nullptr, n_rows, B, C, accumulate, row_counter, s);
+        default: return mub::launch_spmm<128, true>(indptr, pairs, nullptr, n_rows, B, C, accumulate, row_counter, s);
     }
 }

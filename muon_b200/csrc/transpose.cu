@@ -70,6 +70,62 @@ transpose_fill_kernel(const int64_t* __restrict__ indptr, const int32_t* __restr
     }
 }
 
+// Same scatter, but (row, value) is written as ONE 8-byte pair: one scattered store per non-zero instead of
+// two (the fill is bound by the rate of scattered L2 operations, not by bytes).
+__global__ void __launch_bounds__(256)
+transpose_fill_pairs_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            const float* __restrict__ data, int64_t n_rows, int64_t row_offset,
+                            unsigned long long* cursor, int2* __restrict__ t_pairs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t row = warp; row < n_rows; row += n_warps) {
+        const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        const int32_t r = (int32_t)(row + row_offset);
+        int64_t k = s + lane;
+        for (; k + 96 < e; k += 128) {
+            const int c0 = ld_stream(indices + k), c1 = ld_stream(indices + k + 32);
+            const int c2 = ld_stream(indices + k + 64), c3 = ld_stream(indices + k + 96);
+            const float v0 = ld_stream(data + k), v1 = ld_stream(data + k + 32);
+            const float v2 = ld_stream(data + k + 64), v3 = ld_stream(data + k + 96);
+            const unsigned long long s0 = atomicAdd(cursor + c0, 1ull), s1 = atomicAdd(cursor + c1, 1ull);
+            const unsigned long long s2 = atomicAdd(cursor + c2, 1ull), s3 = atomicAdd(cursor + c3, 1ull);
+            t_pairs[s0] = make_int2(r, __float_as_int(v0));
+            t_pairs[s1] = make_int2(r, __float_as_int(v1));
+            t_pairs[s2] = make_int2(r, __float_as_int(v2));
+            t_pairs[s3] = make_int2(r, __float_as_int(v3));
+        }
+        for (; k < e; k += 32) {
+            const int c = ld_stream(indices + k);
+            const float v = ld_stream(data + k);
+            t_pairs[atomicAdd(cursor + c, 1ull)] = make_int2(r, __float_as_int(v));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+row_stats_pairs_kernel(const int64_t* __restrict__ indptr, const int2* __restrict__ pairs, int64_t n_rows,
+                       double* __restrict__ sum, double* __restrict__ sumsq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    for (int64_t row = warp; row < n_rows; row += n_warps) {
+        const int64_t s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+        double a = 0.0, b = 0.0;
+        for (int64_t k = s + lane; k < e; k += 32) {
+            const double v = (double)__int_as_float(ld_stream2(pairs + k).y);
+            a += v;
+            b += v * v;
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) {
+            sum[row] = a;
+            sumsq[row] = b;
+        }
+    }
+}
+
 // per-row sum and sum of squares (fp64 accumulation); applied to the CSR of A^T this yields
 // the per-feature moments MOFA's centring needs (intercepts, muon/_core/tools.py:283-286)
 __global__ void __launch_bounds__(256)
@@ -98,6 +154,36 @@ row_stats_kernel(const int64_t* __restrict__ indptr, const float* __restrict__ d
 }  // namespace mub
 
 extern "C" {
+
+int mub_csr_transpose_fill_pairs(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                                 int32_t n_cols, int64_t row_offset, const int64_t* t_indptr, int64_t* cursor,
+                                 int32_t* t_pairs, mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "transpose_fill_pairs: negative shape");
+    if (n_rows == 0 || n_cols == 0) return 0;
+    MUB_REQUIRE(indptr && t_indptr && cursor && t_pairs, "transpose_fill_pairs: null pointer");
+    MUB_REQUIRE(((uintptr_t)t_pairs & 7) == 0, "transpose_fill_pairs: t_pairs must be 8-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    mub::copy_i64_kernel<<<(n_cols + 255) / 256, 256, 0, s>>>(t_indptr, cursor, n_cols);
+    int64_t want = (n_rows + 7) / 8;
+    int64_t cap = (int64_t)mub::sm_count() * 8;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    mub::transpose_fill_pairs_kernel<<<grid, 256, 0, s>>>(indptr, indices, data, n_rows, row_offset,
+                                                         (unsigned long long*)cursor, (int2*)t_pairs);
+    return mub::check_launch("transpose_fill_pairs");
+}
+
+int mub_csrp_row_stats_f32(const int64_t* indptr, const int32_t* pairs, int64_t n_rows, double* sum, double* sumsq,
+                           mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0, "csrp_row_stats: negative n_rows");
+    if (n_rows == 0) return 0;
+    MUB_REQUIRE(indptr && sum && sumsq, "csrp_row_stats: null pointer");
+    int64_t want = (n_rows + 7) / 8, cap = (int64_t)mub::sm_count() * 8;
+    int grid = (int)(want < cap ? want : cap);
+    mub::row_stats_pairs_kernel<<<grid < 1 ? 1 : grid, 256, 0, (cudaStream_t)stream>>>(indptr, (const int2*)pairs,
+                                                                                     n_rows, sum, sumsq);
+    return mub::check_launch("csrp_row_stats");
+}
 
 int mub_csr_row_stats_f32(const int64_t* indptr, const float* data, int64_t n_rows, double* sum, double* sumsq,
                           mub_stream_t stream) {

@@ -109,6 +109,14 @@ def test_transposed_panels_equal_full_transpose(cuda, monkeypatch):
     monkeypatch.setattr(_device.TransposedPanels, "L2_BUDGET", 700 * 64 * 4)     # force 5 panels
     Tp = _device.TransposedPanels(A, 64)
     assert len(Tp.panels) >= 4 and Tp.panels[0][0] == 0 and Tp.panels[-1][1] == X.shape[0]
+    assert all(isinstance(T, _device.DevicePairs) for _, _, T in Tp.panels)       # 8-byte (index, value) pairs
+    r0, r1, T0 = Tp.panels[1]
+    ref0 = X[r0:r1].T.tocsr()
+    got0 = sp.csr_matrix((T0.data.cpu().numpy(), T0.indices.cpu().numpy(), T0.indptr.cpu().numpy()), shape=T0.shape)
+    got0.sort_indices()
+    ref0.sort_indices()
+    np.testing.assert_array_equal(got0.indices, ref0.indices)
+    np.testing.assert_array_equal(got0.data, ref0.data)
     Y = torch.randn((X.shape[0], 64), device=cuda)
     Z = Tp.spmm(Y)
     ref = X.T.astype(np.float64) @ Y.cpu().numpy().astype(np.float64)
