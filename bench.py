@@ -324,7 +324,7 @@ def main():
                        "cells_total": n_total, "nnz_per_gpu": nnz, "parallelism": f"cells-sharded x{world}",
                        "l2": "inputs (8 B/nnz CSR stream) exceed L2 by >100x; no flush needed",
                        "lsi": {"block": info.block, "iterations": info.iterations, "passes": info.passes,
-                               "tol": args.tol, "converged": info.converged, "max_rel_residual": max(info.residuals),
+                               "tol": args.tol, "converged": info.converged, "stalled": info.stalled, "max_rel_residual": max(info.residuals),
                                "residual_history": [float("%.3g" % h) for h in info.history]}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "phase_ms_per_step": phase_ms, "breakdown_ms": breakdown,

@@ -46,7 +46,8 @@ class SvdInfo:
     basis: int = 0
     block: int = 0
     residuals: list = field(default_factory=list)   # relative residual of the k wanted triplets
-    converged: bool = False
+    converged: bool = False      # all k residuals <= tol (or the Krylov space is the whole space)
+    stalled: bool = False        # stopped because the residuals stopped improving (fp32 floor or clustered spectrum)
     history: list = field(default_factory=list)     # max relative residual per iteration
 
 
@@ -263,7 +264,8 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
             blocks.append((m, m + bn))
             m += bn
         info.basis = m
-        info.converged = done
+        info.converged = (rmax <= tol) or m >= d
+        info.stalled = done and not info.converged
         if done or restart == max_restarts:
             break
         info.restarts += 1

@@ -54,6 +54,10 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     P = _device.pad_width(min(n_comps + 8, 128) if n_comps + 8 <= 128 else n_comps)
     op = CsrOperator(A, P)
     U, s, V, info = truncated_svd(op, n_comps, P, tol=tol, seed=seed)
+    if not info.converged:
+        from warnings import warn
+        warn(f"lsi: stopped after {info.passes} passes at relative residual {max(info.residuals):.1e} > tol={tol:g} "
+             "(clustered singular values around the k-th component?); the leading components are still accurate")
 
     # post-processing of tools.py:60-65 on the device (moments allreduced over cell shards)
     _ph = phase("lsi.post_and_d2h")
