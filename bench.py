@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--peaks", type=int, default=200_000)
     ap.add_argument("--density", type=float, default=0.03)
     ap.add_argument("--k", type=int, default=50)
-    ap.add_argument("--topics", type=int, default=64)
+    ap.add_argument("--topics", type=int, default=0,
+                    help="planted topics of the synthetic matrix (0: max(64, k+28), so that the k wanted components "
+                         "are separated from the noise bulk, SURVEY App. E)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--tol", type=float, default=1e-5)
     ap.add_argument("--sample-cells", type=int, default=2000, help="rows of the CPU-baseline sample")
@@ -157,6 +159,8 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.topics <= 0:
+        args.topics = max(64, args.k + 28)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
