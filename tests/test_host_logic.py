@@ -127,3 +127,17 @@ def test_synth_generator_is_shard_consistent():
     np.testing.assert_array_equal(full.data, stacked.data)
     assert abs(full.nnz / (120 * 700) - 0.05) < 0.01
     assert set(np.unique(full.data)) <= {1.0, 2.0, 3.0, 4.0, 5.0}
+
+
+def test_k_beyond_separated_spectrum_is_reported_not_hidden():
+    """k larger than the number of planted topics: the trailing wanted components sit in the noise bulk
+    (relative gaps ~1e-3), block Lanczos crawls, and the driver must say so (converged=False) instead of
+    silently returning; the separated leading components are still right."""
+    X = tfidf_ref(generate_host(1200, 1000, 0.05, n_topics=6, seed=21)).astype(np.float32)
+    k = 24
+    ref = lsi_ref(X, k, dtype=np.float64)
+    U, s, V, info = truncated_svd(ScipyOperator(X), k, 32, tol=1e-7, max_basis=192, max_restarts=1)
+    assert not info.converged and max(info.residuals) > 1e-7
+    np.testing.assert_allclose(s.numpy()[:6], ref["svalues"][:6], rtol=1e-5)
+    lead = np.abs((V.numpy()[:, :6] * ref["LSI"][:, :6]).sum(0))
+    assert np.all(1 - lead < 1e-6)
