@@ -183,6 +183,8 @@ class SimpleMuData:
         self.update()
 
     def update(self):
+        """Recompute the union of observation / variable names; existing annotation columns are kept
+        (like ``MuData.update_obs``), new names get NaN."""
         names, seen = [], set()
         for a in self.mod.values():
             for nm in a.obs_names:
@@ -190,8 +192,14 @@ class SimpleMuData:
                     seen.add(nm)
                     names.append(nm)
         vnames = [v for a in self.mod.values() for v in a.var_names]
+        old_obs, old_var = getattr(self, "obs", None), getattr(self, "var", None)
         self.obs = _frame(names, len(names), "obs")
         self.var = _frame(vnames, len(vnames), "var")
+        if pd is not None:
+            if isinstance(old_obs, pd.DataFrame) and old_obs.shape[1]:
+                self.obs = old_obs.reindex(self.obs.index)
+            if isinstance(old_var, pd.DataFrame) and old_var.shape[1] and not old_var.index.has_duplicates:
+                self.var = old_var.reindex(self.var.index)
 
     update_obs = update
     update_var = update

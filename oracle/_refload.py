@@ -43,7 +43,7 @@ def _install_stubs():
         mod("mudata", MuData=SimpleMuData)
     if "scanpy" not in sys.modules or getattr(sys.modules["scanpy"], "__stub__", False):
         log = mod("scanpy.logging", info=lambda *a, **k: None, warning=lambda *a, **k: None,
-                  hint=lambda *a, **k: None)
+                  hint=lambda *a, **k: None, debug=lambda *a, **k: None, error=lambda *a, **k: None)
         utils = mod("scanpy._utils", view_to_actual=view_to_actual)
         sc = mod("scanpy", logging=log, _utils=utils)
         sc.__path__ = []  # mark as package so "from scanpy import logging" resolves
@@ -91,3 +91,49 @@ def load_reference_lsi():
     if m is None:
         m = _load("muon/_atac/tools.py", "_refmuon._atac.tools")
     return m.lsi
+
+
+def load_reference_neighbors():
+    """Return the reference's own ``neighbors`` (WNN, muon/_core/preproc.py:264) with its third-party imports
+    (umap, pynndescent, scanpy) replaced by the exact stand-ins of oracle/_third_party.py.  Round-2 oracle for the
+    WNN row: the reference's control flow with exact instead of approximate nearest-neighbour search."""
+    if not reference_available():
+        raise FileNotFoundError(REF_ROOT)
+    _install_stubs()
+    import importlib.metadata as ilm
+
+    from . import _third_party as tp
+
+    def mod(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None or not getattr(m, "__stub__", False):
+            m = types.ModuleType(name)
+            m.__dict__["__stub__"] = True
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        return m
+
+    mod("scanpy.tools")
+    mod("scanpy.tools._utils", _choose_representation=tp.choose_representation)
+    mod("scanpy.neighbors")
+    mod("scanpy.neighbors._connectivity", umap=tp.umap_connectivities)
+    mod("pynndescent")
+    mod("pynndescent.distances", euclidean=tp.euclidean)
+    mod("pynndescent.sparse", sparse_euclidean=tp.sparse_euclidean, sparse_jaccard=tp.sparse_jaccard)
+    mod("umap")
+    mod("umap.umap_", nearest_neighbors=tp.nearest_neighbors)
+    m = sys.modules.get("_refmuon_core_preproc")
+    if m is None:
+        real_version = ilm.version
+
+        def fake_version(name):                     # preproc.py:29-40 branches on the scanpy version
+            return "1.10.4" if name == "scanpy" else real_version(name)
+
+        ilm.version = fake_version
+        try:
+            m = _load("muon/_core/preproc.py", "_refmuon_core_preproc")
+        finally:
+            ilm.version = real_version
+    return m.neighbors

@@ -10,6 +10,7 @@ Outputs (small, committed):
   tfidf_synth.npz   300x400 synthetic counts (float32) + reference output
   lsi_synth.npz     reference lsi() on the TF-IDF of a 600x500 synthetic matrix, k=8
   signatures.json   parameter names/defaults of tfidf, binarize, lsi, mofa (ast, no import)
+  wnn_small.npz     (round-2 groundwork) reference neighbors() with exact-search stand-ins, 150 cells x 2 modalities
 """
 import os
 import sys
@@ -85,6 +86,47 @@ def main():
 
 
 
+def wnn_inputs(N=150, seed=0, k=15):
+    """Two L2-normalised embeddings (8 and 6 dims) of 3 planted clusters + their exact kNN graphs, laid out the
+    way ``sc.pp.neighbors`` leaves them (``obsp["distances"]`` with k-1 entries per row, ``uns["neighbors"]``)."""
+    from oracle import _third_party as tp
+    from muon_b200._containers import SimpleMuData
+    rng = np.random.default_rng(seed)
+    c = rng.integers(0, 3, N)
+    reps = {"rna": rng.normal(size=(N, 8)) + 3 * np.eye(3)[c] @ rng.normal(size=(3, 8)),
+            "atac": rng.normal(size=(N, 6)) + 2 * np.eye(3)[c] @ rng.normal(size=(3, 6))}
+    mods = {}
+    for name, R in reps.items():
+        R = R / np.linalg.norm(R, axis=1, keepdims=True)
+        ad = SimpleAnnData(np.zeros((N, 4)))
+        ad.obsm["X_rep"] = R
+        idx, dist, _ = tp.nearest_neighbors(R, k, "euclidean")
+        ad.obsp["distances"] = sp.csr_matrix((dist[:, 1:].reshape(-1), idx[:, 1:].reshape(-1),
+                                              np.arange(0, N * (k - 1) + 1, k - 1)), shape=(N, N))
+        ad.uns["neighbors"] = {"params": {"n_neighbors": k, "use_rep": "X_rep", "metric": "euclidean"},
+                               "distances_key": "distances", "connectivities_key": "connectivities"}
+        mods[name] = ad
+    return SimpleMuData(mods)
+
+
+def dump_wnn():
+    """Golden for the WNN row (round 2): the reference's own ``neighbors`` control flow
+    (muon/_core/preproc.py:264-640) executed with the exact stand-ins of oracle/_third_party.py."""
+    from oracle._refload import load_reference_neighbors
+    neighbors = load_reference_neighbors()
+    md = wnn_inputs()
+    neighbors(md, n_multineighbors=40)
+    out = {"rep_rna": md.mod["rna"].obsm["X_rep"], "rep_atac": md.mod["atac"].obsm["X_rep"],
+           "w_rna": md.obs["rna:mod_weight"].to_numpy(), "w_atac": md.obs["atac:mod_weight"].to_numpy(),
+           "n_neighbors": np.int64(md.uns["neighbors"]["params"]["n_neighbors"])}
+    out.update(csr_parts(md.mod["rna"].obsp["distances"], "knn_rna"))
+    out.update(csr_parts(md.mod["atac"].obsp["distances"], "knn_atac"))
+    out.update(csr_parts(md.obsp["distances"], "wnn_dist"))
+    out.update(csr_parts(md.obsp["connectivities"], "wnn_conn"))
+    np.savez_compressed(os.path.join(OUT, "wnn_small.npz"), **out)
+    print("wnn_small.npz", os.path.getsize(os.path.join(OUT, "wnn_small.npz")))
+
+
 def dump_signatures():
     """Parameter names and defaults of the three reference entry points, read with ``ast`` (no import):
     muon/_atac/preproc.py::tfidf, ::binarize, muon/_atac/tools.py::lsi, muon/_core/tools.py::mofa."""
@@ -108,6 +150,11 @@ def dump_signatures():
 
 
 if __name__ == "__main__":
-    if "--signatures-only" not in sys.argv:
+    if "--wnn-only" in sys.argv:
+        dump_wnn()
+    elif "--signatures-only" in sys.argv:
+        dump_signatures()
+    else:
         main()
-    dump_signatures()
+        dump_wnn()
+        dump_signatures()
