@@ -160,6 +160,14 @@ int mub_mofa_tau_f32(const float* Praw, const float* mu, const double* zsum, dou
                      const double* ssq, const float* W, const float* WW, double b0, double* b_out, int64_t D,
                      int32_t ld, int32_t K, mub_stream_t stream);
 
+/* ---- exact k-nearest neighbours (groundwork for the WNN row, muon/_core/preproc.py:520-528: the reference asks
+ * umap's NN-descent for n_multineighbors+1 = 201 neighbours per cell and modality; this search is exact).
+ * For every row of X[nq x ld] (d meaningful columns) the k nearest rows of Y[nc x ld] in Euclidean distance,
+ * ascending, ties by lower index; out_idx[nq x k] (-1 if fewer than k candidates), out_dist[nq x k] (not squared).
+ * X == Y is allowed (a point is then its own first neighbour at distance exactly 0).  k <= 320. */
+int mub_knn_l2_f32(const float* X, int64_t nq, const float* Y, int64_t nc, int32_t d, int32_t ld, int32_t k,
+                   int32_t* out_idx, float* out_dist, mub_stream_t stream);
+
 /* ---- synthetic ATAC count generator (benchmark / test input) ---------------
  * Deterministic counter-based planted-topic model; bit-identical to the numpy generator in
  * muon_b200/_synth.py.  Step 1 writes nnz per row; caller scans into indptr; step 2 fills.

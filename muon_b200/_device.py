@@ -456,3 +456,18 @@ def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
         return dev
     except Exception:
         return None
+
+
+def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None):
+    """Exact k nearest neighbours in Euclidean distance (rows of Y closest to each row of X; Y defaults to X).
+    Returns (indices int32 [n x k], distances float32 [n x k]), ascending, ties by lower index.  Groundwork for
+    the WNN row (reference muon/_core/preproc.py:520-528)."""
+    require_cuda()
+    Y = X if Y is None else Y
+    assert X.dtype == torch.float32 and Y.dtype == torch.float32 and X.is_contiguous() and Y.is_contiguous()
+    assert X.shape[1] == Y.shape[1]
+    nq, d = X.shape
+    idx = torch.empty((nq, k), dtype=torch.int32, device=X.device)
+    dist = torch.empty((nq, k), dtype=torch.float32, device=X.device)
+    call("mub_knn_l2_f32", ptr(X), nq, ptr(Y), Y.shape[0], d, d, k, ptr(idx), ptr(dist), stream_ptr())
+    return idx, dist
