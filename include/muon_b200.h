@@ -168,6 +168,24 @@ int mub_mofa_tau_f32(const float* Praw, const float* mu, const double* zsum, dou
 int mub_knn_l2_f32(const float* X, int64_t nq, const float* Y, int64_t nc, int32_t d, int32_t ld, int32_t k,
                    int32_t* out_idx, float* out_dist, mub_stream_t stream);
 
+/* ---- WNN building blocks (muon/_core/preproc.py:264-640; numba helpers :46-159) ------------------------------
+ * bandwidth: for every cell i the n_bw cells minimising the reference's tie-breaking metric
+ *   (N - jd*N) + (bbox - e)/bbox  (jd = Jaccard distance of the kNN sets, e = Euclidean distance; preproc.py:51-76)
+ *   among cells sharing a neighbour with i, enumerated exactly through the transposed kNN graph
+ *   (g_* = kNN graph CSR with sorted rows, t_* = CSR of its transpose); sigma[i] = mean Euclidean distance to
+ *   them (preproc.py:462-470).  status bit0 = a cell had more than 1536 distinct candidates (result invalid).
+ * affinity_topk: union of the per-modality candidate lists cands[m][n x n_cand] (-1 = none), affinity
+ *   sum_m weight[i,m] * exp(-||x^m_i - x^m_j|| / sigmas[m][i]), distance sqrt(0.5 (1 - affinity)) and the n_out
+ *   smallest per cell, ascending (preproc.py:569-604 and _sparse_csr_fast_knn_ :114-135).  reps / dims / lds /
+ *   cands / sigmas are HOST arrays of n_mod device pointers / ints. */
+int mub_wnn_bandwidth_f32(const int64_t* g_indptr, const int32_t* g_indices, const int64_t* t_indptr,
+                          const int32_t* t_indices, const float* X, int64_t n, int32_t d, int32_t ld, int32_t n_bw,
+                          double bbox_norm, double* sigma, int32_t* status, mub_stream_t stream);
+int mub_wnn_affinity_topk_f32(int32_t n_mod, const float* const* reps, const int32_t* dims, const int32_t* lds,
+                              const int32_t* const* cands, const double* const* sigmas, const double* weight,
+                              int64_t n, int32_t n_cand, int32_t n_out, int32_t* out_idx, double* out_dist,
+                              int32_t* status, mub_stream_t stream);
+
 /* ---- synthetic ATAC count generator (benchmark / test input) ---------------
  * Deterministic counter-based planted-topic model; bit-identical to the numpy generator in
  * muon_b200/_synth.py.  Step 1 writes nnz per row; caller scans into indptr; step 2 fills.

@@ -4,11 +4,12 @@
     mu.atac.pp.tfidf(adata)      # muon/_atac/preproc.py:16
     mu.atac.tl.lsi(adata)        # muon/_atac/tools.py:29
     mu.tl.mofa(mdata)            # muon/_core/tools.py:290
+    mu.pp.neighbors(mdata)       # muon/_core/preproc.py:264  (WNN; first version, exact search)
 
 Same signatures and AnnData/MuData slot semantics as the reference; the arithmetic runs in
 hand-written CUDA kernels behind the C ABI in include/muon_b200.h.  There is no CPU fallback.
 """
-from . import atac, tl  # noqa: F401
+from . import atac, pp, tl  # noqa: F401
 from ._containers import SimpleAnnData, SimpleMuData  # noqa: F401
 from ._device import DeviceCSR  # noqa: F401
 

@@ -43,6 +43,8 @@ SIGNATURES = {
     "mub_mofa_update_z_f32": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp],
     "mub_mofa_tau_f32": [vp, vp, vp, f64, vp, vp, vp, vp, f64, vp, i64, i32, i32, vp],
     "mub_knn_l2_f32": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp],
+    "mub_wnn_bandwidth_f32": [vp, vp, vp, vp, vp, i64, i32, i32, i32, f64, vp, vp, vp],
+    "mub_wnn_affinity_topk_f32": [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp],
     "mub_synth_count": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp],
     "mub_synth_fill": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp, vp, vp],
 }

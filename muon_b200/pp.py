@@ -1,0 +1,248 @@
+"""``mu.pp`` -- multimodal preprocessing.  ``neighbors`` (WNN) is the first "next" row of the coverage contract
+(BASELINE configs[4]); status: first correct GPU path, exact instead of approximate search.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from ._containers import is_mudata
+
+
+def _choose_representation(adata, use_rep=None, n_pcs=None):
+    """scanpy.tools._utils._choose_representation for what muon passes (preproc.py:378)."""
+    if use_rep is None or use_rep == "X":
+        if use_rep is None and "X_pca" in adata.obsm and adata.n_vars > 50:
+            X = adata.obsm["X_pca"]
+            return X[:, :n_pcs] if n_pcs else X
+        return adata.X
+    if use_rep in adata.obsm:
+        X = adata.obsm[use_rep]
+        return X[:, :n_pcs] if n_pcs else X
+    raise ValueError(f"Did not find {use_rep} in `.obsm.keys()`.")
+
+
+def _umap_connectivities(knn_idx, knn_dist, n_obs):
+    """UMAP fuzzy simplicial set on a precomputed kNN table (what scanpy's ``umap`` connectivities wrapper
+    returns to preproc.py:607-614): smooth-kNN bandwidths by bisection (64 steps, local_connectivity=1),
+    membership strengths exp(-(d - rho)/sigma), fuzzy union A + A^T - A.A^T.  Vectorised over cells on the device."""
+    import scipy.sparse as sp
+    import torch
+    d = knn_dist.to(torch.float32)
+    n, k = d.shape
+    target = float(np.log2(k))
+    big = torch.finfo(torch.float32).max
+    pos = torch.where(d > 0, d, torch.full_like(d, big))
+    rho = pos.min(dim=1).values
+    rho = torch.where(rho == big, torch.zeros_like(rho), rho)          # no positive distance: rho = 0
+    lo = torch.zeros(n, dtype=torch.float64, device=d.device)
+    hi = torch.full((n,), float("inf"), dtype=torch.float64, device=d.device)
+    mid = torch.ones(n, dtype=torch.float64, device=d.device)
+    done = torch.zeros(n, dtype=torch.bool, device=d.device)
+    dd = (d[:, 1:] - rho[:, None]).to(torch.float64)                   # the first column is skipped (umap: j from 1)
+    for _ in range(64):
+        psum = torch.where(dd > 0, torch.exp(-dd / mid[:, None]), torch.ones_like(dd)).sum(1)
+        done |= (psum - target).abs() < 1e-5
+        gt = psum > target
+        new_hi = torch.where(gt, mid, hi)
+        new_lo = torch.where(gt, lo, mid)
+        new_mid = torch.where(gt, (lo + mid) / 2.0,
+                              torch.where(torch.isinf(hi), mid * 2.0, (mid + hi) / 2.0))
+        hi = torch.where(done, hi, new_hi)
+        lo = torch.where(done, lo, new_lo)
+        mid = torch.where(done, mid, new_mid)
+    sigma = mid.to(torch.float32)
+    mean_row = d.mean(dim=1)
+    mean_all = d.mean()
+    floor = torch.where(rho > 0, 1e-3 * mean_row, 1e-3 * mean_all.expand_as(mean_row))
+    sigma = torch.maximum(sigma, floor)
+    rows = torch.arange(n, device=d.device)[:, None].expand(n, k)
+    val = torch.where((d - rho[:, None] <= 0) | (sigma[:, None] == 0), torch.ones_like(d),
+                      torch.exp(-(d - rho[:, None]) / sigma[:, None]))
+    val = torch.where(knn_idx == rows, torch.zeros_like(val), val)
+    val = torch.where(knn_idx < 0, torch.zeros_like(val), val)
+    A = sp.coo_matrix((val.cpu().numpy().ravel(), (rows.cpu().numpy().ravel(),
+                                                    knn_idx.clamp_min(0).cpu().numpy().ravel())), shape=(n_obs, n_obs))
+    A.eliminate_zeros()
+    A = A.tocsr()
+    At = A.T.tocsr()
+    out = A + At - A.multiply(At)
+    out.eliminate_zeros()
+    return out.tocsr()
+
+
+def neighbors(
+    mdata,
+    n_neighbors: Optional[int] = None,
+    n_bandwidth_neighbors: int = 20,
+    n_multineighbors: int = 200,
+    neighbor_keys: Optional[Dict[str, Optional[str]]] = None,
+    metric: str = "euclidean",
+    low_memory: Optional[bool] = None,
+    key_added: Optional[str] = None,
+    weight_key: Optional[str] = "mod_weight",
+    add_weights_to_modalities: bool = False,
+    eps: float = 1e-4,
+    copy: bool = False,
+    random_state=42,
+):
+    """Multimodal (weighted) nearest-neighbour search -- ``muon.pp.neighbors`` (reference
+    muon/_core/preproc.py:264-640), same arguments and slots: ``obsp[distances/connectivities]``,
+    ``uns[key]``, per-modality cell weights in ``obs["<mod>:mod_weight"]``.
+
+    Differences, all deliberate: every nearest-neighbour search is **exact** (brute force on the GPU) where the
+    reference runs NN-descent, so ``low_memory`` and ``random_state`` have no effect; only the Euclidean metric and
+    dense representations are supported; all modalities must hold the same observations in the same order.
+    """
+    import scipy.sparse as sp
+    import torch
+
+    from . import _device
+    from ._lib import call, ptr, stream_ptr
+
+    if not is_mudata(mdata):
+        raise TypeError("Expected a MuData object")
+    mdata = mdata.copy() if copy else mdata
+    if neighbor_keys is None:
+        modalities = list(mdata.mod.keys())
+        neighbor_keys = {}
+    else:
+        modalities = list(neighbor_keys.keys())
+    if metric != "euclidean":
+        raise NotImplementedError("only metric='euclidean' is supported by the B200 path yet")
+
+    params, reps, mod_reps, mod_n_pcs, mod_k = {}, {}, {}, {}, []
+    for mod in modalities:
+        nkey = neighbor_keys.get(mod, "neighbors")
+        try:
+            nparams = mdata.mod[mod].uns[nkey]
+        except KeyError:
+            raise ValueError(f'Did not find .uns["{nkey}"] for modality "{mod}". Run `sc.pp.neighbors` on all '
+                             "modalities first.")
+        use_rep = nparams["params"].get("use_rep", None)
+        n_pcs = nparams["params"].get("n_pcs", None)
+        mod_k.append(nparams["params"].get("n_neighbors", 0))
+        if nparams["params"].get("metric", "euclidean") != "euclidean" or nparams.get("metric", "euclidean") != "euclidean":
+            raise NotImplementedError("only Euclidean per-modality neighbour graphs are supported yet")
+        params[mod] = nparams
+        R = _choose_representation(mdata.mod[mod], use_rep, n_pcs)
+        if sp.issparse(R):
+            raise NotImplementedError("sparse representations are not supported by the B200 path yet")
+        reps[mod] = np.ascontiguousarray(np.asarray(R), dtype=np.float32)
+        mod_reps[mod] = use_rep if use_rep is not None else -1
+        mod_n_pcs[mod] = n_pcs if n_pcs is not None else -1
+    if n_neighbors is None:
+        ks = np.asarray([k for k in mod_k if k > 0])
+        n_neighbors = int(round(float(np.mean(ks)), 0))
+
+    obs = np.asarray(mdata.obs_names).astype(str)
+    for mod in modalities:
+        if not np.array_equal(np.asarray(mdata.mod[mod].obs_names).astype(str), obs):
+            raise NotImplementedError("modalities with different observations are not supported by the B200 path yet")
+    N, M = len(obs), len(modalities)
+    if M > 4:
+        raise NotImplementedError("more than 4 modalities")
+
+    _device.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = stream_ptr()
+    Xd, Gd, nnd, sig = {}, {}, {}, {}
+    for mod in modalities:
+        G = sp.csr_matrix(mdata.mod[mod].obsp[params[mod]["distances_key"]])
+        deg = np.diff(G.indptr)
+        if np.any(deg == 0):
+            i = int(np.where(deg == 0)[0][0])
+            raise ValueError(f"Cell {i} in modality {mod} does not have any neighbors. This could be due to subsetting "
+                             "after nearest neighbors calculation. Make sure to subset before calculating nearest neighbors.")
+        nnd[mod] = torch.from_numpy(np.minimum.reduceat(G.data.astype(np.float64), G.indptr[:-1])).to(dev)
+        Gd[mod] = _device.DeviceCSR.from_scipy(G, dtype=np.float32)
+        Xd[mod] = torch.from_numpy(reps[mod]).to(dev)
+
+    # ---- kernel bandwidths sigma (preproc.py:408-470) ----------------------------------------------------------
+    for mod in modalities:
+        X = Xd[mod]
+        bbox = float(np.linalg.norm(np.ptp(reps[mod].astype(np.float64), axis=0), ord=2))
+        Gt = _device.csr_transpose(Gd[mod])
+        s = torch.empty(N, dtype=torch.float64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        call("mub_wnn_bandwidth_f32", ptr(Gd[mod].indptr), ptr(Gd[mod].indices), ptr(Gt.indptr), ptr(Gt.indices),
+             ptr(X), N, X.shape[1], X.shape[1], n_bandwidth_neighbors, bbox, ptr(s), ptr(status), st)
+        if int(status[0]) != 0:
+            raise RuntimeError("neighbors: a cell shares kNN neighbours with more than 1536 cells (hub); not supported yet")
+        sig[mod] = s
+
+    # ---- modality weights (preproc.py:472-508) -----------------------------------------------------------------
+    ratios = torch.full((N, M), float("-inf"), dtype=torch.float64, device=dev)
+    for i1, m1 in enumerate(modalities):
+        X = Xd[m1]
+        d = X.shape[1]
+        P = _device.pad_width(d)
+        Xp = torch.zeros((N, P), dtype=torch.float32, device=dev)
+        Xp[:, :d] = X
+        cur, others = None, []
+        for i2, m2 in enumerate(modalities):
+            G2 = Gd[m2]
+            deg = (G2.indptr[1:] - G2.indptr[:-1]).to(torch.float32)
+            mean_graph = G2.with_data(torch.repeat_interleave(1.0 / deg, (G2.indptr[1:] - G2.indptr[:-1])))
+            r = _device.spmm(mean_graph, Xp, dynamic=False)[:, :d]       # mean of X over the cell's neighbours in m2
+            dist = (X.to(torch.float64) - r.to(torch.float64)).norm(dim=1)
+            theta = torch.exp(-torch.clamp(dist - nnd[m1], min=0) / (sig[m1] - nnd[m1]))
+            if i1 == i2:
+                cur = theta
+            else:
+                others.append(theta)
+        best_other = torch.stack(others, 1).max(dim=1).values if others else torch.full_like(cur, float("-inf"))
+        ratios[:, i1] = cur / (best_other + eps)
+    weights = torch.softmax(ratios, dim=1).contiguous()
+
+    # ---- candidates: n_multineighbors exact neighbours per modality (preproc.py:509-567) ----------------------
+    cands = []
+    for mod in modalities:
+        idx, _ = _device.knn_l2(Xd[mod], min(n_multineighbors + 1, N))
+        cands.append(idx[:, 1:].contiguous())                            # drop the cell itself (preproc.py:531)
+    n_cand = cands[0].shape[1]
+
+    # ---- weighted affinities over the union of candidates, top n_neighbors+1 (preproc.py:569-604) --------------
+    import ctypes as C
+    n_out = n_neighbors + 1
+    out_idx = torch.empty((N, n_out), dtype=torch.int32, device=dev)
+    out_dist = torch.empty((N, n_out), dtype=torch.float64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    arr_p = (C.c_void_p * M)
+    reps_p = arr_p(*[Xd[m].data_ptr() for m in modalities])
+    cands_p = arr_p(*[c.data_ptr() for c in cands])
+    sig_p = arr_p(*[sig[m].data_ptr() for m in modalities])
+    dims_p = (C.c_int32 * M)(*[Xd[m].shape[1] for m in modalities])
+    call("mub_wnn_affinity_topk_f32", M, reps_p, dims_p, dims_p, cands_p, sig_p, ptr(weights), N, n_cand, n_out,
+         ptr(out_idx), ptr(out_dist), ptr(status), st)
+    if int(status[0]) != 0:
+        raise RuntimeError("neighbors: candidate union overflow")
+    if bool((out_idx < 0).any()):
+        raise ValueError("neighbors: fewer candidates than n_neighbors + 1; increase n_multineighbors")
+
+    indptr = np.arange(0, (N + 1) * n_out, n_out)
+    distances = sp.csr_matrix((out_dist.cpu().numpy().ravel(), out_idx.cpu().numpy().ravel().astype(np.int64), indptr),
+                              shape=(N, N))
+    connectivities = _umap_connectivities(out_idx.to(torch.int64), out_dist, N)
+
+    if key_added is None:
+        key_added, conns_key, dists_key = "neighbors", "connectivities", "distances"
+    else:
+        conns_key, dists_key = f"{key_added}_connectivities", f"{key_added}_distances"
+    W = weights.cpu().numpy()
+    for i, m in enumerate(modalities):
+        if weight_key:
+            if add_weights_to_modalities:
+                mdata.mod[m].obs[weight_key] = W[:, i]
+            else:
+                mdata.obs[":".join([m, weight_key])] = W[:, i]
+    mdata.obsp[dists_key] = distances
+    mdata.obsp[conns_key] = connectivities
+    mdata.uns[key_added] = {
+        "connectivities_key": conns_key, "distances_key": dists_key,
+        "params": {"n_neighbors": n_neighbors, "n_multineighbors": n_multineighbors, "metric": metric, "eps": eps,
+                   "random_state": random_state, "use_rep": mod_reps, "n_pcs": mod_n_pcs, "method": "umap"},
+    }
+    mdata.update_obs()
+    return mdata if copy else None

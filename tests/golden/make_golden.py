@@ -135,7 +135,7 @@ def dump_signatures():
     from oracle._refload import REF_ROOT
     out = {}
     for rel, names in (("muon/_atac/preproc.py", ("tfidf", "binarize")), ("muon/_atac/tools.py", ("lsi",)),
-                       ("muon/_core/tools.py", ("mofa",))):
+                       ("muon/_core/tools.py", ("mofa",)), ("muon/_core/preproc.py", ("neighbors",))):
         tree = ast.parse(open(os.path.join(REF_ROOT, rel)).read())
         for node in tree.body:
             if isinstance(node, ast.FunctionDef) and node.name in names:

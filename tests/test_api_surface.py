@@ -11,7 +11,7 @@ from conftest import GOLDEN
 
 
 @pytest.mark.parametrize("name,fn", [("tfidf", mu.atac.pp.tfidf), ("binarize", mu.atac.pp.binarize),
-                                     ("lsi", mu.atac.tl.lsi), ("mofa", mu.tl.mofa)])
+                                     ("lsi", mu.atac.tl.lsi), ("mofa", mu.tl.mofa), ("neighbors", mu.pp.neighbors)])
 def test_signature_matches_reference(name, fn):
     ref = json.load(open(os.path.join(GOLDEN, "signatures.json")))[name]
     if name == "mofa":

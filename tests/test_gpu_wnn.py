@@ -1,0 +1,69 @@
+"""GPU: mu.pp.neighbors (WNN) against the golden produced by the reference's own driver
+(muon/_core/preproc.py:264-640) executed with exact-search stand-ins (tests/golden/make_golden.py::dump_wnn)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import muon_b200 as mu
+from conftest import golden_csr, load_golden
+from muon_b200._containers import SimpleAnnData, SimpleMuData
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(z):
+    mods = {}
+    for name in ("rna", "atac"):
+        R = z[f"rep_{name}"]
+        ad = SimpleAnnData(np.zeros((R.shape[0], 4)))
+        ad.obsm["X_rep"] = R
+        ad.obsp["distances"] = golden_csr(z, f"knn_{name}")
+        ad.uns["neighbors"] = {"params": {"n_neighbors": 15, "use_rep": "X_rep", "metric": "euclidean"},
+                               "distances_key": "distances", "connectivities_key": "connectivities"}
+        mods[name] = ad
+    return SimpleMuData(mods)
+
+
+def test_wnn_matches_reference_driver_golden(cuda):
+    z = load_golden("wnn_small.npz")
+    md = _inputs(z)
+    assert mu.pp.neighbors(md, n_multineighbors=40) is None
+    n = z["rep_rna"].shape[0]
+    np.testing.assert_allclose(md.obs["rna:mod_weight"].to_numpy(), z["w_rna"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(md.obs["atac:mod_weight"].to_numpy(), z["w_atac"], rtol=2e-5, atol=1e-7)
+    got = sp.csr_matrix(md.obsp["distances"])
+    k1 = int(z["n_neighbors"]) + 1
+    assert np.all(np.diff(got.indptr) == k1)
+    assert np.all(np.diff(got.data.reshape(n, k1), axis=1) >= 0)          # ascending per row (numba argsort order)
+    got.sort_indices()
+    ref = golden_csr(z, "wnn_dist")
+    same_rows = np.array([np.array_equal(got.indices[got.indptr[i]:got.indptr[i + 1]],
+                                         ref.indices[ref.indptr[i]:ref.indptr[i + 1]]) for i in range(n)])
+    assert same_rows.mean() > 0.98                                        # fp32 embeddings: a tie may flip at the k-th place
+    rows = np.where(same_rows)[0]
+    for i in rows[:: max(1, len(rows) // 50)]:
+        np.testing.assert_allclose(got.data[got.indptr[i]:got.indptr[i + 1]], ref.data[ref.indptr[i]:ref.indptr[i + 1]],
+                                   rtol=1e-5, atol=1e-7)
+    C = sp.csr_matrix(md.obsp["connectivities"])
+    Cr = golden_csr(z, "wnn_conn")
+    assert (C != C.T).nnz == 0
+    if same_rows.all():
+        assert abs(C - Cr).max() < 1e-4
+    p = md.uns["neighbors"]["params"]
+    assert p["n_neighbors"] == int(z["n_neighbors"]) and p["n_multineighbors"] == 40 and p["method"] == "umap"
+
+
+def test_wnn_argument_errors(cuda):
+    z = load_golden("wnn_small.npz")
+    md = _inputs(z)
+    del md.mod["atac"].uns["neighbors"]
+    with pytest.raises(ValueError):
+        mu.pp.neighbors(md)
+    with pytest.raises(TypeError):
+        mu.pp.neighbors(np.ones((3, 3)))
+    md = _inputs(z)
+    with pytest.raises(NotImplementedError):
+        mu.pp.neighbors(md, metric="cosine")
+    out = mu.pp.neighbors(md, n_multineighbors=30, key_added="wnn", add_weights_to_modalities=True, copy=True)
+    assert "wnn_distances" in out.obsp and "wnn" in out.uns and "mod_weight" in out.mod["rna"].obs.columns
+    assert "wnn_distances" not in md.obsp
