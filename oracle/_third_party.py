@@ -12,7 +12,7 @@ module restates just those call targets:
   (how pynndescent invokes custom distances) on the float32-converted data.  Parity against the real package can
   therefore only be statistical; exact-vs-exact it is deterministic.
 * ``euclidean``, ``sparse_euclidean``, ``sparse_jaccard`` -- pynndescent.distances / pynndescent.sparse, written as
-  plain Python so that muon can ``njit`` them itself (preproc.py:46-48).  Index arrays are sorted (scipy CSR rows).
+  plain Python so that muon can ``njit`` them itself (preproc.py:46-48); index arrays need not be sorted.
 * ``choose_representation`` -- scanpy.tools._utils._choose_representation for explicit ``use_rep`` (and X fallback).
 * ``umap_connectivities`` -- scanpy.neighbors._connectivity.umap = umap.umap_.fuzzy_simplicial_set on precomputed
   kNN with set_op_mix_ratio=1, local_connectivity=1 (McInnes et al. 2018, Algorithm 2/3), returned as CSR.
@@ -34,7 +34,10 @@ def euclidean(x, y):
 
 
 def sparse_jaccard(ind1, data1, ind2, data2):
-    """1 - |A n B| / |A u B| on the index sets (values ignored, as in pynndescent)."""
+    """1 - |A n B| / |A u B| on the index sets (values ignored, as in pynndescent, whose arr_union /
+    arr_intersect do not assume sorted input either)."""
+    ind1 = np.sort(ind1)
+    ind2 = np.sort(ind2)
     i1 = 0
     i2 = 0
     n_equal = 0
@@ -56,6 +59,9 @@ def sparse_jaccard(ind1, data1, ind2, data2):
 
 
 def sparse_euclidean(ind1, data1, ind2, data2):
+    o1 = np.argsort(ind1)
+    o2 = np.argsort(ind2)
+    ind1, data1, ind2, data2 = ind1[o1], data1[o1], ind2[o2], data2[o2]
     i1 = 0
     i2 = 0
     acc = 0.0
