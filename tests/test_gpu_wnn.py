@@ -67,3 +67,39 @@ def test_wnn_argument_errors(cuda):
     out = mu.pp.neighbors(md, n_multineighbors=30, key_added="wnn", add_weights_to_modalities=True, copy=True)
     assert "wnn_distances" in out.obsp and "wnn" in out.uns and "mod_weight" in out.mod["rna"].obs.columns
     assert "wnn_distances" not in md.obsp
+
+
+def test_wnn_second_case_vs_numpy_restatement(cuda):
+    """Different sizes / k / candidate counts than the golden: CUDA path vs oracle/wnn_ref.py."""
+    from oracle import _third_party as tp
+    from oracle.wnn_ref import wnn_ref
+    rng = np.random.default_rng(3)
+    N, k = 260, 10
+    c = rng.integers(0, 4, N)
+    reps = [rng.normal(size=(N, 12)) + 2.5 * np.eye(4)[c] @ rng.normal(size=(4, 12)),
+            rng.normal(size=(N, 5)) + 2.0 * np.eye(4)[c] @ rng.normal(size=(4, 5))]
+    reps = [(r / np.linalg.norm(r, axis=1, keepdims=True)).astype(np.float32).astype(np.float64) for r in reps]
+    mods, graphs = {}, []
+    for name, R in zip(("a", "b"), reps):
+        idx, dist, _ = tp.nearest_neighbors(R, k, "euclidean")
+        g = sp.csr_matrix((dist[:, 1:].reshape(-1), idx[:, 1:].reshape(-1), np.arange(0, N * (k - 1) + 1, k - 1)),
+                          shape=(N, N))
+        graphs.append(g)
+        ad = SimpleAnnData(np.zeros((N, 2)))
+        ad.obsm["X_emb"] = R
+        ad.obsp["d"] = g
+        ad.uns["nn"] = {"params": {"n_neighbors": k, "use_rep": "X_emb"}, "distances_key": "d"}
+        mods[name] = ad
+    md = SimpleMuData(mods)
+    mu.pp.neighbors(md, n_multineighbors=25, n_bandwidth_neighbors=12, neighbor_keys={"a": "nn", "b": "nn"})
+    ref = wnn_ref(reps, graphs, n_neighbors=k, n_bandwidth_neighbors=12, n_multineighbors=25)
+    np.testing.assert_allclose(md.obs["a:mod_weight"].to_numpy(), ref["weights"][:, 0], rtol=2e-5, atol=1e-7)
+    got = sp.csr_matrix(md.obsp["distances"])
+    got.sort_indices()
+    rd = ref["distances"].copy()
+    rd.sort_indices()
+    same = np.array([np.array_equal(got.indices[got.indptr[i]:got.indptr[i + 1]], rd.indices[rd.indptr[i]:rd.indptr[i + 1]])
+                     for i in range(N)])
+    assert same.mean() > 0.98
+    i = int(np.where(same)[0][0])
+    np.testing.assert_allclose(got.data[got.indptr[i]:got.indptr[i + 1]], rd.data[rd.indptr[i]:rd.indptr[i + 1]], rtol=1e-5)

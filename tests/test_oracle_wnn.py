@@ -64,3 +64,17 @@ def test_reference_neighbors_reproduces_golden():
     ref = golden_csr(z, "wnn_dist")
     np.testing.assert_array_equal(got.indices, ref.indices)
     np.testing.assert_allclose(got.data, ref.data, rtol=1e-10, atol=1e-12)
+
+
+def test_numpy_restatement_reproduces_reference_driver_golden():
+    from oracle.wnn_ref import wnn_ref
+    z = load_golden("wnn_small.npz")
+    r = wnn_ref([z["rep_rna"], z["rep_atac"]], [golden_csr(z, "knn_rna"), golden_csr(z, "knn_atac")],
+                int(z["n_neighbors"]), n_multineighbors=40)
+    np.testing.assert_allclose(r["weights"][:, 0], z["w_rna"], rtol=1e-12)
+    got = r["distances"].copy()
+    got.sort_indices()
+    ref = golden_csr(z, "wnn_dist")
+    np.testing.assert_array_equal(got.indices, ref.indices)
+    np.testing.assert_allclose(got.data, ref.data, rtol=1e-10, atol=1e-14)
+    assert abs(r["connectivities"] - golden_csr(z, "wnn_conn")).max() < 1e-6
