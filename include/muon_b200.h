@@ -173,14 +173,21 @@ int mub_knn_l2_f32(const float* X, int64_t nq, const float* Y, int64_t nc, int32
  *   (N - jd*N) + (bbox - e)/bbox  (jd = Jaccard distance of the kNN sets, e = Euclidean distance; preproc.py:51-76)
  *   among cells sharing a neighbour with i, enumerated exactly through the transposed kNN graph
  *   (g_* = kNN graph CSR with sorted rows, t_* = CSR of its transpose); sigma[i] = mean Euclidean distance to
- *   them (preproc.py:462-470).  status bit0 = a cell had more than 1536 distinct candidates (result invalid).
+ *   them (preproc.py:462-470).  First pass: cell_list = NULL (tables in shared memory); cells sharing neighbours
+ *   with more than 1536 cells get sigma = -1 and status bit0, and are redone by a second call with cell_list
+ *   (status bit1 = even the fallback tables were too small).
  * affinity_topk: union of the per-modality candidate lists cands[m][n x n_cand] (-1 = none), affinity
  *   sum_m weight[i,m] * exp(-||x^m_i - x^m_j|| / sigmas[m][i]), distance sqrt(0.5 (1 - affinity)) and the n_out
  *   smallest per cell, ascending (preproc.py:569-604 and _sparse_csr_fast_knn_ :114-135).  reps / dims / lds /
  *   cands / sigmas are HOST arrays of n_mod device pointers / ints. */
 int mub_wnn_bandwidth_f32(const int64_t* g_indptr, const int32_t* g_indices, const int64_t* t_indptr,
                           const int32_t* t_indices, const float* X, int64_t n, int32_t d, int32_t ld, int32_t n_bw,
-                          double bbox_norm, double* sigma, int32_t* status, mub_stream_t stream);
+                          double bbox_norm, double* sigma, int32_t* status, const int64_t* cell_list,
+                          int64_t n_cells, void* workspace, int32_t table_slots, int32_t n_tables,
+                          mub_stream_t stream);
+/* fallback pass for hub cells: cell_list[n_cells] = cells with sigma == -1 after the first pass, hash tables of
+ * table_slots (power of two) entries in `workspace` (mub_wnn_bandwidth_workspace_bytes(table_slots, n_tables)) */
+size_t mub_wnn_bandwidth_workspace_bytes(int32_t table_slots, int32_t n_tables);
 int mub_wnn_affinity_topk_f32(int32_t n_mod, const float* const* reps, const int32_t* dims, const int32_t* lds,
                               const int32_t* const* cands, const double* const* sigmas, const double* weight,
                               int64_t n, int32_t n_cand, int32_t n_out, int32_t* out_idx, double* out_dist,

@@ -30,20 +30,25 @@ struct WarpTable {
     int32_t* cnt;    // [H]
     float* aux;      // [H]  per-candidate float (Euclidean distance / affinity distance)
     int32_t* aux2;   // [H]  per-candidate int (|S_j|)
-    uint16_t* list;  // [kWnnMaxCand] occupied slots in insertion order
+    int32_t* list;   // [max_cand] occupied slots in insertion order
+    int H;           // slots (power of two): kWnnH in shared memory, larger in the global-memory fallback
+    int shift;       // 32 - log2(H)
+    int max_cand;
 };
 
-__device__ __forceinline__ uint32_t wnn_hash(int32_t j) { return ((uint32_t)j * 2654435761u) >> (32 - 11); }
+__device__ __forceinline__ uint32_t wnn_hash(const WarpTable& t, int32_t j) {
+    return ((uint32_t)j * 2654435761u) >> t.shift;
+}
 
 // insert j (count += 1); returns false on overflow.  Called by any subset of lanes.
 __device__ __forceinline__ bool table_insert(const WarpTable& t, int32_t j, int* n_list) {
-    uint32_t h = wnn_hash(j);
-    for (int probe = 0; probe < kWnnH; ++probe) {
+    uint32_t h = wnn_hash(t, j);
+    for (int probe = 0; probe < t.H; ++probe) {
         const int32_t old = atomicCAS(&t.key[h], -1, j);
         if (old == -1) {  // new candidate
             const int pos = atomicAdd(n_list, 1);
-            if (pos >= kWnnMaxCand) return false;
-            t.list[pos] = (uint16_t)h;
+            if (pos >= t.max_cand) return false;
+            t.list[pos] = (int32_t)h;
             atomicAdd(&t.cnt[h], 1);
             return true;
         }
@@ -51,18 +56,18 @@ __device__ __forceinline__ bool table_insert(const WarpTable& t, int32_t j, int*
             atomicAdd(&t.cnt[h], 1);
             return true;
         }
-        h = (h + 1) & (kWnnH - 1);
+        h = (h + 1) & (t.H - 1);
     }
     return false;
 }
 
 __device__ __forceinline__ int table_find(const WarpTable& t, int32_t j) {
-    uint32_t h = wnn_hash(j);
-    for (int probe = 0; probe < kWnnH; ++probe) {
+    uint32_t h = wnn_hash(t, j);
+    for (int probe = 0; probe < t.H; ++probe) {
         const int32_t k = t.key[h];
         if (k == j) return (int)h;
         if (k == -1) return -1;
-        h = (h + 1) & (kWnnH - 1);
+        h = (h + 1) & (t.H - 1);
     }
     return -1;
 }
@@ -76,36 +81,49 @@ __device__ __forceinline__ float row_dist(const float* __restrict__ a, const flo
     return (float)sqrt(s);
 }
 
-__device__ __forceinline__ WarpTable carve(unsigned char* base, int warp) {
-    constexpr size_t per = sizeof(int32_t) * kWnnH * 3 + sizeof(float) * kWnnH + sizeof(uint16_t) * kWnnMaxCand + 16;
-    unsigned char* p = base + (size_t)warp * per;
+__host__ __device__ inline size_t table_bytes(int H, int max_cand) {
+    return sizeof(int32_t) * (size_t)H * 3 + sizeof(float) * (size_t)H + sizeof(int32_t) * (size_t)max_cand + 16;
+}
+__device__ __forceinline__ WarpTable carve(unsigned char* base, int slot, int H, int max_cand) {
+    unsigned char* p = base + (size_t)slot * table_bytes(H, max_cand);
     WarpTable t;
     t.key = reinterpret_cast<int32_t*>(p);
-    t.cnt = t.key + kWnnH;
-    t.aux2 = t.cnt + kWnnH;
-    t.aux = reinterpret_cast<float*>(t.aux2 + kWnnH);
-    t.list = reinterpret_cast<uint16_t*>(t.aux + kWnnH);
+    t.cnt = t.key + H;
+    t.aux2 = t.cnt + H;
+    t.aux = reinterpret_cast<float*>(t.aux2 + H);
+    t.list = reinterpret_cast<int32_t*>(t.aux + H);
+    t.H = H;
+    t.shift = 32 - (31 - __clz(H));
+    t.max_cand = max_cand;
     return t;
 }
-constexpr size_t kWnnSmemPerWarp = sizeof(int32_t) * kWnnH * 3 + sizeof(float) * kWnnH + sizeof(uint16_t) * kWnnMaxCand + 16;
+constexpr size_t kWnnSmemPerWarp = sizeof(int32_t) * kWnnH * 3 + sizeof(float) * kWnnH + sizeof(int32_t) * kWnnMaxCand + 16;
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWnnWarps * 32)
 wnn_bandwidth_kernel(const int64_t* __restrict__ g_indptr, const int32_t* __restrict__ g_indices,
                      const int64_t* __restrict__ t_indptr, const int32_t* __restrict__ t_indices,
                      const float* __restrict__ X, int64_t n, int d, int ld, int n_bw, double bbox,
-                     double* __restrict__ sigma, int32_t* __restrict__ status) {
+                     double* __restrict__ sigma, int32_t* __restrict__ status,
+                     const int64_t* __restrict__ cell_list, int64_t n_list_cells, unsigned char* gtable, int gH,
+                     int gmax) {
+    // Fast path: cell_list == NULL, tables in shared memory (kWnnH slots).  Fallback for hub cells: cell_list
+    // holds the cells whose candidate set overflowed, tables live in global memory (gH slots per warp).
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int n_list_s[kWnnWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpTable T = carve(smem_raw, warp);
+    const bool big = (cell_list != nullptr);
+    const WarpTable T = big ? carve(gtable, blockIdx.x * kWnnWarps + warp, gH, gmax)
+                            : carve(smem_raw, warp, kWnnH, kWnnMaxCand);
     int* n_list = &n_list_s[warp];
     const double Nd = (double)n;
-    for (int h = lane; h < kWnnH; h += 32) { T.key[h] = -1; T.cnt[h] = 0; }
+    for (int h = lane; h < T.H; h += 32) { T.key[h] = -1; T.cnt[h] = 0; }
     if (lane == 0) *n_list = 0;
     __syncwarp();
 
-    for (int64_t i = (int64_t)blockIdx.x * kWnnWarps + warp; i < n; i += (int64_t)gridDim.x * kWnnWarps) {
+    const int64_t n_work = big ? n_list_cells : n;
+    for (int64_t w = (int64_t)blockIdx.x * kWnnWarps + warp; w < n_work; w += (int64_t)gridDim.x * kWnnWarps) {
+        const int64_t i = big ? cell_list[w] : w;
         const int64_t s0 = g_indptr[i], s1 = g_indptr[i + 1];
         const int si = (int)(s1 - s0);
         bool ok = true;
@@ -119,10 +137,9 @@ wnn_bandwidth_kernel(const int64_t* __restrict__ g_indptr, const int32_t* __rest
             }
         }
         __syncwarp();
-        if (!__all_sync(0xffffffffu, ok) || *n_list > kWnnMaxCand) {
-            if (lane == 0) atomicOr(status, 1);
-        }
-        const int nc = min(*n_list, kWnnMaxCand);
+        const bool overflow = !__all_sync(0xffffffffu, ok) || *n_list > T.max_cand;
+        if (overflow && lane == 0) atomicOr(status, big ? 2 : 1);   // bit0: needs the fallback, bit1: fallback too small
+        const int nc = min(*n_list, T.max_cand);
         // 2. per candidate: |S_j| and the Euclidean distance to i
         const float* xi = X + (size_t)i * ld;
         for (int c = lane; c < nc; c += 32) {
@@ -167,7 +184,7 @@ wnn_bandwidth_kernel(const int64_t* __restrict__ g_indptr, const int32_t* __rest
             esum += (double)row_dist(xi, X + (size_t)j * ld, d);
             ++taken;
         }
-        if (lane == 0) sigma[i] = esum / (double)n_bw;
+        if (lane == 0) sigma[i] = overflow ? -1.0 : esum / (double)n_bw;   // -1: recomputed by the fallback pass
         // 5. reset the touched slots
         __syncwarp();
         for (int c = lane; c < nc; c += 32) {
@@ -175,8 +192,8 @@ wnn_bandwidth_kernel(const int64_t* __restrict__ g_indptr, const int32_t* __rest
             T.key[h] = -1;
             T.cnt[h] = 0;
         }
-        if (*n_list > kWnnMaxCand) {                 // overflowed: clear everything
-            for (int h = lane; h < kWnnH; h += 32) { T.key[h] = -1; T.cnt[h] = 0; }
+        if (overflow) {                              // clear everything
+            for (int h = lane; h < T.H; h += 32) { T.key[h] = -1; T.cnt[h] = 0; }
         }
         __syncwarp();
         if (lane == 0) *n_list = 0;
@@ -200,7 +217,7 @@ wnn_affinity_topk_kernel(WnnMods M, const double* __restrict__ weight, int64_t n
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int n_list_s[kWnnWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const WarpTable T = carve(smem_raw, warp);
+    const WarpTable T = carve(smem_raw, warp, kWnnH, kWnnMaxCand);
     int* n_list = &n_list_s[warp];
     for (int h = lane; h < kWnnH; h += 32) { T.key[h] = -1; T.cnt[h] = 0; }
     if (lane == 0) *n_list = 0;
@@ -294,9 +311,15 @@ static int wnn_grid(int64_t n) {
 
 extern "C" {
 
+size_t mub_wnn_bandwidth_workspace_bytes(int32_t table_slots, int32_t n_tables) {
+    return mub::table_bytes(table_slots, table_slots / 2) * (size_t)n_tables;
+}
+
 int mub_wnn_bandwidth_f32(const int64_t* g_indptr, const int32_t* g_indices, const int64_t* t_indptr,
                           const int32_t* t_indices, const float* X, int64_t n, int32_t d, int32_t ld, int32_t n_bw,
-                          double bbox_norm, double* sigma, int32_t* status, mub_stream_t stream) {
+                          double bbox_norm, double* sigma, int32_t* status, const int64_t* cell_list,
+                          int64_t n_cells, void* workspace, int32_t table_slots, int32_t n_tables,
+                          mub_stream_t stream) {
     MUB_REQUIRE(n >= 0 && d >= 1 && ld >= d && n_bw >= 1, "wnn_bandwidth: bad arguments");
     if (n == 0) return 0;
     MUB_REQUIRE(g_indptr && g_indices && t_indptr && t_indices && X && sigma && status, "wnn_bandwidth: null pointer");
@@ -306,9 +329,23 @@ int mub_wnn_bandwidth_f32(const int64_t* g_indptr, const int32_t* g_indices, con
         mub::set_error("wnn_bandwidth: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
         return -2;
     }
-    mub::wnn_bandwidth_kernel<<<mub::wnn_grid(n), mub::kWnnWarps * 32, smem, (cudaStream_t)stream>>>(
-        g_indptr, g_indices, t_indptr, t_indices, X, n, d, ld, n_bw, bbox_norm, sigma, status);
-    return mub::check_launch("wnn_bandwidth");
+    if (cell_list == nullptr) {
+        mub::wnn_bandwidth_kernel<<<mub::wnn_grid(n), mub::kWnnWarps * 32, smem, (cudaStream_t)stream>>>(
+            g_indptr, g_indices, t_indptr, t_indices, X, n, d, ld, n_bw, bbox_norm, sigma, status, nullptr, 0,
+            nullptr, 0, 0);
+        return mub::check_launch("wnn_bandwidth");
+    }
+    // fallback for hub cells: big tables in caller-provided global memory, n_tables warps
+    if (n_cells <= 0) return 0;
+    MUB_REQUIRE(workspace && table_slots >= 1024 && (table_slots & (table_slots - 1)) == 0 && n_tables >= mub::kWnnWarps,
+                "wnn_bandwidth: fallback needs a workspace, a power-of-two table size and >= 4 tables");
+    int grid = n_tables / mub::kWnnWarps;
+    const int64_t want = (n_cells + mub::kWnnWarps - 1) / mub::kWnnWarps;
+    if (grid > want) grid = (int)want;
+    mub::wnn_bandwidth_kernel<<<grid, mub::kWnnWarps * 32, smem, (cudaStream_t)stream>>>(
+        g_indptr, g_indices, t_indptr, t_indices, X, n, d, ld, n_bw, bbox_norm, sigma, status, cell_list, n_cells,
+        (unsigned char*)workspace, table_slots, table_slots / 2);
+    return mub::check_launch("wnn_bandwidth_fallback");
 }
 
 int mub_wnn_affinity_topk_f32(int32_t n_mod, const float* const* reps, const int32_t* dims, const int32_t* lds,

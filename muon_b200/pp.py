@@ -167,9 +167,19 @@ def neighbors(
         s = torch.empty(N, dtype=torch.float64, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         call("mub_wnn_bandwidth_f32", ptr(Gd[mod].indptr), ptr(Gd[mod].indices), ptr(Gt.indptr), ptr(Gt.indices),
-             ptr(X), N, X.shape[1], X.shape[1], n_bandwidth_neighbors, bbox, ptr(s), ptr(status), st)
-        if int(status[0]) != 0:
-            raise RuntimeError("neighbors: a cell shares kNN neighbours with more than 1536 cells (hub); not supported yet")
+             ptr(X), N, X.shape[1], X.shape[1], n_bandwidth_neighbors, bbox, ptr(s), ptr(status), None, 0, None, 0, 0, st)
+        if int(status[0]) & 1:
+            # hub cells (sharing neighbours with > 1536 cells): redo them with big hash tables in global memory
+            from ._lib import load
+            hubs = torch.nonzero(s < 0).reshape(-1).contiguous()
+            slots, tables = 1 << 18, 64
+            ws = torch.empty(int(load().mub_wnn_bandwidth_workspace_bytes(slots, tables)), dtype=torch.uint8, device=dev)
+            status.zero_()
+            call("mub_wnn_bandwidth_f32", ptr(Gd[mod].indptr), ptr(Gd[mod].indices), ptr(Gt.indptr), ptr(Gt.indices),
+                 ptr(X), N, X.shape[1], X.shape[1], n_bandwidth_neighbors, bbox, ptr(s), ptr(status), ptr(hubs),
+                 hubs.numel(), ptr(ws), slots, tables, st)
+            if int(status[0]) & 2:
+                raise RuntimeError("neighbors: a cell shares kNN neighbours with more than 131072 cells")
         sig[mod] = s
 
     # ---- modality weights (preproc.py:472-508) -----------------------------------------------------------------

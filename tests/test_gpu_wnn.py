@@ -103,3 +103,38 @@ def test_wnn_second_case_vs_numpy_restatement(cuda):
     assert same.mean() > 0.98
     i = int(np.where(same)[0][0])
     np.testing.assert_allclose(got.data[got.indptr[i]:got.indptr[i + 1]], rd.data[rd.indptr[i]:rd.indptr[i + 1]], rtol=1e-5)
+
+
+def test_wnn_hub_cells_take_the_global_table_fallback(cuda):
+    """A cell that is everybody's neighbour makes every candidate set N-1 > 1536 cells: the shared-memory tables
+    overflow and the bandwidth kernel's second pass (hash tables in global memory) must give the same sigma /
+    weights as the exhaustive numpy restatement."""
+    from oracle import _third_party as tp
+    from oracle.wnn_ref import wnn_ref
+    rng = np.random.default_rng(11)
+    N, k = 1700, 8
+    c = rng.integers(0, 5, N)
+    reps = [rng.normal(size=(N, 10)) + 2.5 * np.eye(5)[c] @ rng.normal(size=(5, 10)),
+            rng.normal(size=(N, 6)) + 2.0 * np.eye(5)[c] @ rng.normal(size=(5, 6))]
+    reps = [(r / np.linalg.norm(r, axis=1, keepdims=True)).astype(np.float32).astype(np.float64) for r in reps]
+    mods, graphs = {}, []
+    for m, (name, R) in enumerate(zip(("a", "b"), reps)):
+        idx, dist, _ = tp.nearest_neighbors(R, k, "euclidean")
+        idx, dist = idx[:, 1:].copy(), dist[:, 1:].copy()
+        if m == 0:                                             # plant the hub: cell 0 replaces the farthest neighbour
+            for i in range(1, N):
+                if 0 not in idx[i]:
+                    idx[i, -1] = 0
+                    dist[i, -1] = np.linalg.norm(R[i] - R[0])
+        g = sp.csr_matrix((dist.reshape(-1), idx.reshape(-1), np.arange(0, N * (k - 1) + 1, k - 1)), shape=(N, N))
+        graphs.append(g)
+        ad = SimpleAnnData(np.zeros((N, 2)))
+        ad.obsm["X_emb"] = R
+        ad.obsp["d"] = g
+        ad.uns["nn"] = {"params": {"n_neighbors": k, "use_rep": "X_emb"}, "distances_key": "d"}
+        mods[name] = ad
+    md = SimpleMuData(mods)
+    mu.pp.neighbors(md, n_multineighbors=30, neighbor_keys={"a": "nn", "b": "nn"})
+    ref = wnn_ref(reps, graphs, n_neighbors=k, n_multineighbors=30)
+    np.testing.assert_allclose(md.obs["a:mod_weight"].to_numpy(), ref["weights"][:, 0], rtol=5e-5, atol=1e-6)
+    np.testing.assert_allclose(md.obs["b:mod_weight"].to_numpy(), ref["weights"][:, 1], rtol=5e-5, atol=1e-6)
