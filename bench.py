@@ -99,6 +99,20 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def onchip_roofline(nnz, P, ms_per_pass, sm_mhz, n_sms=148):
+    """Second roofline of the SpMM kernel: every non-zero moves 4*P bytes of the dense operand plus its 8-byte
+    {index, value} entry through the SM's L1/LSU data path (128 B/clk/SM, shared with shared-memory traffic), so
+    at P=64 a pass cannot take less than ~2 clocks per non-zero per SM however little DRAM traffic it causes.
+    Reported next to the HBM figure because this, not DRAM, is what the kernel saturates."""
+    if not sm_mhz or not ms_per_pass or ms_per_pass != ms_per_pass:
+        return None
+    bytes_per_pass = float(nnz) * (4.0 * P + 8.0)
+    peak = n_sms * 128.0 * sm_mhz * 1e6 / 1e12                     # TB/s
+    ach = bytes_per_pass / (ms_per_pass * 1e-3) / 1e12
+    return {"bound": "l1-lsu data path (128 B/clk/SM)", "achieved": ach, "peak": peak, "unit": "TB/s",
+            "frac": ach / peak, "bytes_per_nnz": 4.0 * P + 8.0, "sm_mhz": sm_mhz, "sms": n_sms}
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -259,6 +273,9 @@ def main():
         t = float(np.mean(tf_red) + np.mean(tf_app))
         roofline["tfidf"] = {"achieved": 20.0 * nnz / (t * 1e-3) / 1e9, "unit": "GB/s", "ms": t,
                              "frac": 20.0 * nnz / (t * 1e-3) / 1e9 / hbm}
+    if rank == 0 and clocks and spmm_ms:
+        roofline["onchip"] = onchip_roofline(nnz, P, spmm_total / max(n_pass, 1), clocks.get("sm_mhz"),
+                                             torch.cuda.get_device_properties(local).multi_processor_count)
     phase_ms = {name: float(np.sum(v)) / args.steps for name, v in kern.items()}
 
     breakdown = None

@@ -272,21 +272,19 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
         V0, _ = torch.linalg.qr(V0_next)
 
     # ---- final Rayleigh-Ritz polish, as scipy does after ARPACK (_svds.py:508-533) -------------
-    _ph = phase("lsi.final")
-    _ph.__enter__()
-    Vk, _ = _qr_dspace(op, Vk, P)
-    Vk = Vk.contiguous()
-    kk = Vk.shape[1]
-    Y = op.av(_pad(Vk, P))
-    info.passes += 1
-    G = op.gram(Y, kk)
-    lam, Z = torch.linalg.eigh(0.5 * (G + G.T))
-    lam, Z = lam.flip(0), Z.flip(1)
-    s = lam.clamp_min(0).sqrt()
-    Zs = (Z / s.clamp_min(1e-300)).to(torch.float32)
-    Mz = torch.zeros((P, kk), dtype=torch.float32, device=dev)
-    Mz[:kk, :] = Zs
-    Uk = Y @ Mz
-    Vk = Vk @ Z.to(torch.float32)
-    _ph.__exit__(None, None, None)
+    with phase("lsi.final"):
+        Vk, _ = _qr_dspace(op, Vk, P)
+        Vk = Vk.contiguous()
+        kk = Vk.shape[1]
+        Y = op.av(_pad(Vk, P))
+        info.passes += 1
+        G = op.gram(Y, kk)
+        lam, Z = torch.linalg.eigh(0.5 * (G + G.T))
+        lam, Z = lam.flip(0), Z.flip(1)
+        s = lam.clamp_min(0).sqrt()
+        Zs = (Z / s.clamp_min(1e-300)).to(torch.float32)
+        Mz = torch.zeros((P, kk), dtype=torch.float32, device=dev)
+        Mz[:kk, :] = Zs
+        Uk = Y @ Mz
+        Vk = Vk @ Z.to(torch.float32)
     return Uk, s, Vk, info

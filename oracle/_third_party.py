@@ -185,6 +185,9 @@ def umap_connectivities(knn_indices, knn_dists, *, n_obs, n_neighbors, set_op_mi
     n, k = knn_indices.shape
     rows = np.repeat(np.arange(n), k)
     cols = knn_indices.reshape(-1).astype(np.int64)
+    missing = cols == -1                 # umap leaves rows/cols/vals of missing slots at 0 (entry (0, 0) += 0)
+    rows[missing] = 0
+    cols[missing] = 0
     vals = np.zeros(n * k, dtype=np.float32)
     for i in range(n):
         for j in range(k):

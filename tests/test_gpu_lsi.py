@@ -83,3 +83,23 @@ def test_lsi_dense_input_and_mudata(cuda):
     mu.atac.tl.lsi(md, n_comps=6)
     assert ad.obsm["X_lsi"].dtype == np.float64 and ad.varm["LSI"].shape == (300, 6)
     np.testing.assert_allclose(ad.uns["lsi"]["stdev"], ref["stdev"], rtol=1e-5)
+
+
+def test_lsi_does_not_reuse_the_device_copy_after_a_host_edit(cuda):
+    """tfidf() on a host matrix leaves a device twin behind for lsi(); one edited value on the host (anywhere,
+    not only at the sampled positions) must invalidate it."""
+    from muon_b200 import _device
+    C = generate_host(3000, 900, 0.05, n_topics=8, seed=4)
+    ad = SimpleAnnData(C.copy())
+    mu.atac.pp.tfidf(ad)
+    assert _device.recall_resident(ad.X) is not None
+    nnz = ad.X.nnz
+    sampled = set(np.linspace(0, nnz - 1, num=min(nnz, 4096), dtype=np.int64).tolist())
+    j = next(i for i in range(12345, nnz) if i not in sampled)  # a position the sampled fingerprint does not look at
+    ad.X.data[j] *= 1.5
+    assert _device.recall_resident(ad.X) is None
+    ad.X.data[:400] *= 30.0                                      # make the edit visible in the spectrum
+    mu.atac.tl.lsi(ad, n_comps=6)
+    fresh = SimpleAnnData(ad.X.copy())
+    mu.atac.tl.lsi(fresh, n_comps=6)
+    np.testing.assert_allclose(ad.uns["lsi"]["stdev"], fresh.uns["lsi"]["stdev"], rtol=1e-6)

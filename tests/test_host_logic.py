@@ -141,3 +141,29 @@ def test_k_beyond_separated_spectrum_is_reported_not_hidden():
     np.testing.assert_allclose(s.numpy()[:6], ref["svalues"][:6], rtol=1e-5)
     lead = np.abs((V.numpy()[:, :6] * ref["LSI"][:, :6]).sum(0))
     assert np.all(1 - lead < 1e-6)
+
+
+def test_resident_copy_checksum_sees_any_single_value_edit():
+    """lsi() reuses the device copy left by tfidf() only if every host value still matches it: the 64-bit
+    checksum of the raw bits must agree between the numpy and the torch implementation and change with any edit."""
+    import torch
+    from muon_b200 import _device as d
+    for n in (0, 1, 7, 8, 9, 1_000_003):
+        a = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+        h = d._bits_checksum_host(a)
+        assert h == d._bits_checksum_device(torch.from_numpy(a))
+        if n:
+            b = a.copy()
+            b[n // 3] = np.nextafter(b[n // 3], np.float32(9))
+            assert d._bits_checksum_host(b) != h
+
+
+def test_bench_onchip_roofline_arithmetic():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = bench.onchip_roofline(nnz=6_000_000_000, P=64, ms_per_pass=88.0, sm_mhz=1920.0)
+    assert abs(r["peak"] - 148 * 128 * 1.92e9 / 1e12) < 1e-9 and r["bytes_per_nnz"] == 264.0
+    assert abs(r["achieved"] - 6e9 * 264 / 0.088 / 1e12) < 1e-9 and 0.45 < r["frac"] < 0.55
+    assert bench.onchip_roofline(1, 64, float("nan"), 1900.0) is None and bench.onchip_roofline(1, 64, 1.0, None) is None

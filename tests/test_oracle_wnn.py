@@ -78,3 +78,23 @@ def test_numpy_restatement_reproduces_reference_driver_golden():
     np.testing.assert_array_equal(got.indices, ref.indices)
     np.testing.assert_allclose(got.data, ref.data, rtol=1e-10, atol=1e-14)
     assert abs(r["connectivities"] - golden_csr(z, "wnn_conn")).max() < 1e-6
+
+
+def test_product_umap_connectivities_match_the_standin_on_cpu_tensors():
+    """muon_b200.pp._umap_connectivities is plain torch (no custom kernel), so its arithmetic can be checked without
+    a GPU against oracle/_third_party.py::umap_connectivities (= scanpy's umap connectivities wrapper)."""
+    import torch
+    from muon_b200.pp import _umap_connectivities
+    from oracle import _third_party as tp
+    rng = np.random.default_rng(5)
+    n, k = 300, 12
+    X = rng.normal(size=(n, 6)) + 3.0 * np.eye(6)[rng.integers(0, 6, n)]
+    idx, dist, _ = tp.nearest_neighbors(X, k, "euclidean")
+    dist = dist.astype(np.float32)
+    dist[7, 1:4] = dist[7, 1]                       # ties at rho
+    idx[11, -1] = -1                                # a missing neighbour slot
+    ref = tp.umap_connectivities(idx, dist, n_obs=n, n_neighbors=k)
+    got = _umap_connectivities(torch.from_numpy(idx), torch.from_numpy(dist), n)
+    assert (got != got.T).nnz == 0
+    assert abs(got - ref).max() < 2e-5
+    assert got.nnz == ref.nnz
