@@ -509,10 +509,14 @@ def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
         return None
 
 
-def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None):
+def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Optional[str] = None):
     """Exact k nearest neighbours in Euclidean distance (rows of Y closest to each row of X; Y defaults to X).
     Returns (indices int32 [n x k], distances float32 [n x k]), ascending, ties by lower index.  Groundwork for
-    the WNN row (reference muon/_core/preproc.py:520-528)."""
+    the WNN row (reference muon/_core/preproc.py:520-528).
+
+    algo: "simt" (fp32 CUDA-core kernel), "tc" (tcgen05 TF32 candidate pass + fp32 re-rank, same result; falls back
+    to "simt" -- another GPU kernel, not the host -- if a query has too many points inside the TF32 error band)
+    or None = $MUON_B200_KNN, default "simt"."""
     require_cuda()
     Y = X if Y is None else Y
     assert X.dtype == torch.float32 and Y.dtype == torch.float32 and X.is_contiguous() and Y.is_contiguous()
@@ -520,5 +524,20 @@ def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None):
     nq, d = X.shape
     idx = torch.empty((nq, k), dtype=torch.int32, device=X.device)
     dist = torch.empty((nq, k), dtype=torch.float32, device=X.device)
+    algo = os.environ.get("MUON_B200_KNN", "simt") if algo is None else algo
+    if algo == "tc" and d <= 128 and k <= 512:
+        nbytes = int(load().mub_knn_l2_tc_workspace_bytes(nq, Y.shape[0]))
+        ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=X.device)
+        status = torch.zeros(1, dtype=torch.int32, device=X.device)
+        call("mub_knn_l2_tc_f32", ptr(X), nq, ptr(Y), Y.shape[0], d, d, k, ptr(idx), ptr(dist), ptr(ws), nbytes,
+             ptr(status), stream_ptr())
+        st = int(status[0])
+        if st & 4:
+            raise MuonB200Error("knn_l2(algo='tc'): tcgen05 commit never arrived (internal error)")
+        if st == 0:
+            return idx, dist
+        # st & 2: error band too crowded for some query -> exact SIMT kernel below
+    elif algo not in ("simt", "tc"):
+        raise ValueError(f"unknown kNN algorithm {algo!r}")
     call("mub_knn_l2_f32", ptr(X), nq, ptr(Y), Y.shape[0], d, d, k, ptr(idx), ptr(dist), stream_ptr())
     return idx, dist

@@ -43,6 +43,7 @@ SIGNATURES = {
     "mub_mofa_update_z_f32": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp],
     "mub_mofa_tau_f32": [vp, vp, vp, f64, vp, vp, vp, vp, f64, vp, i64, i32, i32, vp],
     "mub_knn_l2_f32": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp],
+    "mub_knn_l2_tc_f32": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp, vp],
     "mub_wnn_bandwidth_f32": [vp, vp, vp, vp, vp, i64, i32, i32, i32, f64, vp, vp, vp, i64, vp, i32, i32, vp],
     "mub_wnn_affinity_topk_f32": [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp],
     "mub_synth_count": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp],
@@ -52,6 +53,7 @@ SPECIAL_RESTYPE = {
     "mub_last_error": ([], C.c_char_p),
     "mub_gram_workspace_bytes": ([i64, i32], C.c_size_t),
     "mub_wnn_bandwidth_workspace_bytes": ([i32, i32], C.c_size_t),
+    "mub_knn_l2_tc_workspace_bytes": ([i64, i64], C.c_size_t),
 }
 
 TFIDF_LOG_TF, TFIDF_LOG_IDF, TFIDF_LOG_TFIDF, TFIDF_NO_SCALE, TFIDF_BINARIZE = 1, 2, 4, 8, 16

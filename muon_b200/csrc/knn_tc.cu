@@ -1,0 +1,387 @@
+// Exact k-nearest-neighbour search, tensor-core candidate pass + fp32 re-rank (tcgen05 / TMEM, sm_100a).
+//
+// Same contract as knn.cu (mub_knn_l2_f32): the k nearest rows of Y for every row of X in Euclidean distance,
+// ascending, ties by lower index, distances bit-identical to the SIMT kernel.  The n x n inner-product matrix is
+// the one GEMM-shaped operation of the WNN row (reference muon/_core/preproc.py:520-528), so it runs on the 5th-gen
+// tensor cores:
+//
+//   pass 1  knn_tc_candidates_kernel: one CTA owns 128 queries (M = 128 = the TMEM lanes).  Candidate tiles of 128
+//           points are written to shared memory in the canonical no-swizzle K-major layout (8-row x 16-byte core
+//           matrices, SBO 128 B, LBO 2048 B; validated by experimental/umma_probe.cu), one elected thread issues
+//           ceil(d/8) tcgen05.mma.kind::tf32 instructions that accumulate S = Q C^T in 128 TMEM columns and commits
+//           to an mbarrier; the 128 threads then read their own row of S with tcgen05.ld (thread t = TMEM lane t),
+//           form a(q,c) = |c|^2 - 2 S and keep every candidate with a <= tau_q in a per-query buffer.
+//           TF32 truncates the inputs to 10 mantissa bits, so a() carries an error of at most 2^-8 |q||c|; the
+//           threshold is therefore tau_q = (k-th smallest a seen so far, rounded up) + 2 * bound.  Order statistics
+//           move by at most the perturbation, hence no true k-nearest neighbour is ever rejected.
+//           When a buffer fills up (1024 entries) the warp re-derives tau by bisection on the float keys and drops
+//           what no longer qualifies.
+//   pass 2  knn_tc_rerank_kernel: warp per query, exact fp32 squared distances of the surviving candidates with the
+//           same arithmetic as knn.cu (sequential fmaf over the dimensions), k rounds of (distance, index) minimum
+//           extraction.
+//
+// First version: single-stage (load -> MMA -> epilogue in sequence; two CTAs per SM overlap each other), plain
+// global->shared copies instead of TMA.  Every mbarrier wait is bounded; a timeout is reported through `status`.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mub {
+
+constexpr int kTcM = 128;        // queries per CTA tile = TMEM lanes
+constexpr int kTcN = 128;        // candidates per MMA tile = TMEM columns
+constexpr int kTcCap = 1024;     // candidate buffer entries per query
+constexpr int kTcThreads = 128;
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, K-major, no swizzle (cute/arch/mma_sm100_desc.hpp bit layout)
+__device__ __forceinline__ uint64_t tc_umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;                                    // descriptor version 1 (Blackwell)
+    return d;
+}
+
+// monotone map float -> uint32 (order preserving, total on non-NaN)
+__device__ __forceinline__ uint32_t tc_okey(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float tc_from_okey(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void knn_tc_norms_kernel(const float* __restrict__ X, int64_t n, int d, int ld, float* __restrict__ norms,
+                                    unsigned int* __restrict__ maxbits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int t = 0; t < d; ++t) {
+        const float v = X[(size_t)i * ld + t];
+        s = fmaf(v, v, s);
+    }
+    norms[i] = s;
+    if (maxbits) atomicMax(maxbits, __float_as_uint(s));   // s >= 0: the bit pattern is monotone
+}
+
+// Re-derive tau from the buffer (k-th smallest key, rounded up to a 2^12-ulp bucket, plus the slack) and drop the
+// entries above it.  Called warp-wide; every lane works on its own column of the [cap][128] buffers.
+__device__ __forceinline__ void tc_compact(float* __restrict__ kb, int32_t* __restrict__ ib, int tid, int k, float slack,
+                                           int& cnt, float& tau) {
+    if (cnt >= k) {
+        uint32_t lo = 0, hi = 0xFFFFFu;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int i = 0; i < cnt; ++i) c += ((tc_okey(kb[(size_t)i * kTcM + tid]) >> 12) <= mid) ? 1 : 0;
+            if (c >= k) hi = mid; else lo = mid + 1;
+        }
+        float base = tc_from_okey((lo << 12) | 0xFFFu);   // upper end of the bucket holding the k-th smallest key
+        if (!(base <= FLT_MAX)) base = FLT_MAX;            // bucket top beyond the finite range (or NaN pattern)
+        tau = base + slack;
+        int w = 0;
+        for (int i = 0; i < cnt; ++i) {
+            const float v = kb[(size_t)i * kTcM + tid];
+            if (v <= tau) {
+                const int32_t j = ib[(size_t)i * kTcM + tid];
+                kb[(size_t)w * kTcM + tid] = v;
+                ib[(size_t)w * kTcM + tid] = j;
+                ++w;
+            }
+        }
+        cnt = w;
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+knn_tc_candidates_kernel(const float* __restrict__ X, const float* __restrict__ xnorm, int64_t nq,
+                         const float* __restrict__ Y, const float* __restrict__ ynorm, int64_t nc, int d, int ld, int Kp,
+                         int k, const unsigned int* __restrict__ ymax_bits, float* __restrict__ kbuf,
+                         int32_t* __restrict__ ibuf, int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt,
+                         int32_t* __restrict__ status) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunks = Kp / 4;                                  // 16-byte K chunks (4 tf32 values)
+    unsigned char* sQ = smem;                                   // [chunks][128][16 B]
+    unsigned char* sC = smem + (size_t)chunks * kTcM * 16;      // [chunks][128][16 B]
+    float* sCn = reinterpret_cast<float*>(sC + (size_t)chunks * kTcN * 16);   // [2][128] candidate norms
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(kTcN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_s;
+
+    float* kb = kbuf + (size_t)blockIdx.x * kTcCap * kTcM;
+    int32_t* ib = ibuf + (size_t)blockIdx.x * kTcCap * kTcM;
+    const float cmax = sqrtf(__uint_as_float(*ymax_bits));
+    uint32_t idesc = 0;
+    idesc |= 1u << 4;                                           // accumulator f32
+    idesc |= 2u << 7;                                           // A = tf32
+    idesc |= 2u << 10;                                          // B = tf32
+    idesc |= (uint32_t)(kTcN >> 3) << 17;
+    idesc |= (uint32_t)(kTcM >> 4) << 24;
+
+    const int64_t n_qt = (nq + kTcM - 1) / kTcM;
+    uint32_t it = 0;                                            // MMA batches issued so far (mbarrier phase = it & 1)
+    bool dead = false;
+    for (int64_t qt = blockIdx.x; qt < n_qt && !dead; qt += gridDim.x) {
+        const int64_t row = qt * kTcM + tid;
+        const bool live = row < nq;
+        for (int c = 0; c < chunks; ++c) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int dim = c * 4 + e;
+                v[e] = (live && dim < d) ? __ldg(X + (size_t)row * ld + dim) : 0.f;
+            }
+            *reinterpret_cast<float4*>(sQ + ((size_t)c * kTcM + tid) * 16) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        const float qn = live ? xnorm[row] : 0.f;
+        // 2 x (error bound of a() = 2^-8 |q| max|c|), doubled again for safety, plus fp32 rounding of the norms
+        const float slack = 4.f * 0.00390625f * sqrtf(qn) * cmax + 1e-5f * (qn + cmax * cmax);
+        float tau = live ? INFINITY : -INFINITY;
+        int cnt = 0;
+        int overflow = 0;
+
+        for (int64_t c0 = 0; c0 < nc; c0 += kTcN, ++it) {
+            if (__any_sync(0xffffffffu, cnt > kTcCap - kTcN)) {
+                tc_compact(kb, ib, tid, k, slack, cnt, tau);
+                if (cnt > kTcCap - kTcN) {                      // more than 896 candidates inside the slack band
+                    overflow = 1;
+                    cnt = kTcCap - kTcN;
+                }
+            }
+            const int64_t crow = c0 + tid;
+            const bool cl = crow < nc;
+            for (int c = 0; c < chunks; ++c) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int dim = c * 4 + e;
+                    v[e] = (cl && dim < d) ? __ldg(Y + (size_t)crow * ld + dim) : 0.f;
+                }
+                *reinterpret_cast<float4*>(sC + ((size_t)c * kTcN + tid) * 16) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            float* cn = sCn + (it & 1) * kTcN;
+            cn[tid] = cl ? ynorm[crow] : INFINITY;
+            asm volatile("fence.proxy.async.shared::cta;");     // generic stores -> async proxy (tensor core reads)
+            asm volatile("tcgen05.fence::before_thread_sync;"); // orders the previous tile's tcgen05.ld before the barrier
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (tid == 0) {
+                const uint32_t lbo = kTcM * 16, sbo = 128;
+                for (int ks = 0; ks < Kp / 8; ++ks) {
+                    const uint64_t da = tc_umma_desc(tc_smem_u32(sQ) + (uint32_t)(2 * ks) * kTcM * 16, lbo, sbo);
+                    const uint64_t db = tc_umma_desc(tc_smem_u32(sC) + (uint32_t)(2 * ks) * kTcN * 16, lbo, sbo);
+                    const uint32_t acc = ks > 0 ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_base),
+                                 "l"(da), "l"(db), "r"(idesc), "r"(acc));
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(&bar))
+                             : "memory");
+            }
+            uint32_t done = 0;
+            for (int spin = 0; spin < (1 << 22) && !done; ++spin) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(done)
+                             : "r"(tc_smem_u32(&bar)), "r"(it & 1u)
+                             : "memory");
+            }
+            if (__syncthreads_or(done ? 0 : 1)) {               // the commit never arrived: give up, report
+                dead = true;
+                break;
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int cc = 0; cc < kTcN; cc += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc;
+                __syncwarp();                                   // tcgen05.ld is .sync.aligned: reconverge after the appends
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                    "%15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float a = fmaf(-2.f, __uint_as_float(r[j]), cn[cc + j]);
+                    if (a <= tau && c0 + cc + j < nc) {
+                        if (cnt < kTcCap) {
+                            kb[(size_t)cnt * kTcM + tid] = a;
+                            ib[(size_t)cnt * kTcM + tid] = (int32_t)(c0 + cc + j);
+                            ++cnt;
+                        } else {
+                            overflow = 1;
+                        }
+                    }
+                }
+            }
+        }
+        if (dead) break;
+        tc_compact(kb, ib, tid, k, slack, cnt, tau);            // final trim
+        if (live) {
+            cand_cnt[row] = cnt;
+            for (int i = 0; i < cnt; ++i) cand[(size_t)row * kTcCap + i] = ib[(size_t)i * kTcM + tid];
+            if (overflow) atomicOr(status, 2);
+        }
+    }
+    if (dead && tid == 0) atomicOr(status, 4);
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTcN));
+    }
+}
+
+constexpr int kTcRerankWarps = 4;
+
+__global__ void __launch_bounds__(kTcRerankWarps * 32)
+knn_tc_rerank_kernel(const float* __restrict__ X, int64_t nq, const float* __restrict__ Y, int d, int ld, int k,
+                     const int32_t* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
+                     int32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+    __shared__ float sd_all[kTcRerankWarps][kTcCap];
+    __shared__ int32_t si_all[kTcRerankWarps][kTcCap];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * kTcRerankWarps + warp;
+    if (row >= nq) return;
+    float* sd = sd_all[warp];
+    int32_t* si = si_all[warp];
+    int n = cand_cnt[row];
+    n = n < 0 ? 0 : (n > kTcCap ? kTcCap : n);
+    const float* xq = X + (size_t)row * ld;
+    for (int i = lane; i < n; i += 32) {
+        const int32_t j = cand[(size_t)row * kTcCap + i];
+        const float* yc = Y + (size_t)j * ld;
+        float acc = 0.f;
+        for (int t = 0; t < d; ++t) {                           // same arithmetic as knn.cu: sequential fmaf of differences
+            const float df = __ldg(xq + t) - __ldg(yc + t);
+            acc = fmaf(df, df, acc);
+        }
+        sd[i] = acc;
+        si[i] = j;
+    }
+    __syncwarp();
+    for (int r = 0; r < k; ++r) {
+        float bm = FLT_MAX;
+        int bp = -1, bi = 0x7fffffff;
+        for (int t = lane; t < n; t += 32) {
+            const float x = sd[t];
+            const int xi = si[t];
+            if (xi >= 0 && (bp < 0 || x < bm || (x == bm && xi < bi))) { bm = x; bp = t; bi = xi; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, bm, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (op >= 0 && (bp < 0 || om < bm || (om == bm && oi < bi))) { bm = om; bp = op; bi = oi; }
+        }
+        if (lane == 0) {
+            if (bp >= 0) {
+                out_idx[(size_t)row * k + r] = bi;
+                out_dist[(size_t)row * k + r] = sqrtf(bm);
+                si[bp] = -1;
+            } else {
+                out_idx[(size_t)row * k + r] = -1;
+                out_dist[(size_t)row * k + r] = INFINITY;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+struct TcLayout {
+    size_t xnorm, ynorm, ymax, cnt, cand, kbuf, ibuf, total;
+    int grid;
+};
+
+static TcLayout tc_layout(int64_t nq, int64_t nc) {
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    TcLayout L;
+    const int64_t n_qt = (nq + kTcM - 1) / kTcM;
+    int g = 2 * sm_count();
+    if (g > n_qt) g = (int)(n_qt > 0 ? n_qt : 1);
+    L.grid = g;
+    size_t o = 0;
+    L.xnorm = o; o = up(o + sizeof(float) * (size_t)nq);
+    L.ynorm = o; o = up(o + sizeof(float) * (size_t)nc);
+    L.ymax = o;  o = up(o + 256);
+    L.cnt = o;   o = up(o + sizeof(int32_t) * (size_t)nq);
+    L.cand = o;  o = up(o + sizeof(int32_t) * (size_t)nq * kTcCap);
+    L.kbuf = o;  o = up(o + sizeof(float) * (size_t)g * kTcCap * kTcM);
+    L.ibuf = o;  o = up(o + sizeof(int32_t) * (size_t)g * kTcCap * kTcM);
+    L.total = o;
+    return L;
+}
+
+}  // namespace mub
+
+extern "C" {
+
+size_t mub_knn_l2_tc_workspace_bytes(int64_t nq, int64_t nc) {
+    if (nq < 0 || nc < 0) return 0;
+    return mub::tc_layout(nq, nc).total;
+}
+
+int mub_knn_l2_tc_f32(const float* X, int64_t nq, const float* Y, int64_t nc, int32_t d, int32_t ld, int32_t k,
+                      int32_t* out_idx, float* out_dist, void* workspace, size_t workspace_bytes, int32_t* status,
+                      mub_stream_t stream) {
+    MUB_REQUIRE(nq >= 0 && nc >= 0 && d >= 1 && ld >= d, "knn_l2_tc: bad shape");
+    MUB_REQUIRE(d <= 128, "knn_l2_tc: d <= 128 (got %d)", d);
+    MUB_REQUIRE(k >= 1 && k <= 512, "knn_l2_tc: need 1 <= k <= 512 (got %d)", k);
+    MUB_REQUIRE(nc < (int64_t)1 << 31, "knn_l2_tc: more than 2^31 candidates");
+    if (nq == 0) return 0;
+    MUB_REQUIRE(X && Y && out_idx && out_dist && workspace && status, "knn_l2_tc: null pointer");
+    const mub::TcLayout L = mub::tc_layout(nq, nc);
+    MUB_REQUIRE(workspace_bytes >= L.total, "knn_l2_tc: workspace of %zu B, need %zu B", workspace_bytes, L.total);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    float* xnorm = (float*)(ws + L.xnorm);
+    float* ynorm = (float*)(ws + L.ynorm);
+    unsigned int* ymax = (unsigned int*)(ws + L.ymax);
+    int32_t* cnt = (int32_t*)(ws + L.cnt);
+    int32_t* cand = (int32_t*)(ws + L.cand);
+    float* kbuf = (float*)(ws + L.kbuf);
+    int32_t* ibuf = (int32_t*)(ws + L.ibuf);
+    cudaError_t e = cudaMemsetAsync(ymax, 0, 4, s);
+    if (e != cudaSuccess) {
+        mub::set_error("knn_l2_tc: memset: %s", cudaGetErrorString(e));
+        return -2;
+    }
+    mub::knn_tc_norms_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(X, nq, d, ld, xnorm, nullptr);
+    if (nc > 0) mub::knn_tc_norms_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(Y, nc, d, ld, ynorm, ymax);
+    const int Kp = (d + 7) / 8 * 8;
+    const size_t smem = (size_t)(Kp / 4) * (mub::kTcM + mub::kTcN) * 16 + 2 * mub::kTcN * sizeof(float);
+    e = cudaFuncSetAttribute(mub::knn_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        mub::set_error("knn_l2_tc: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        return -2;
+    }
+    mub::knn_tc_candidates_kernel<<<L.grid, mub::kTcThreads, smem, s>>>(X, xnorm, nq, Y, ynorm, nc, d, ld, Kp, k, ymax, kbuf,
+                                                                         ibuf, cand, cnt, status);
+    int rc = mub::check_launch("knn_l2_tc candidates");
+    if (rc) return rc;
+    mub::knn_tc_rerank_kernel<<<(unsigned)((nq + mub::kTcRerankWarps - 1) / mub::kTcRerankWarps), mub::kTcRerankWarps * 32, 0, s>>>(
+        X, nq, Y, d, ld, k, cand, cnt, out_idx, out_dist);
+    return mub::check_launch("knn_l2_tc rerank");
+}
+
+}  // extern "C"
