@@ -171,9 +171,9 @@ int mub_knn_l2_f32(const float* X, int64_t nq, const float* Y, int64_t nc, int32
 /* Same result (bit-identical indices and distances), tensor-core version: tcgen05 TF32 inner products in TMEM select
  * the candidates (threshold widened by the TF32 error bound so that no true neighbour is lost), an fp32 pass with
  * the arithmetic of mub_knn_l2_f32 ranks them.  d <= 128, k <= 512.  `workspace` of
- * mub_knn_l2_tc_workspace_bytes(nq, nc) bytes; *status (zeroed by the caller) gets bit1 if some query had more than
+ * mub_knn_l2_tc_workspace_bytes(nq, nc, d) bytes; *status (zeroed by the caller) gets bit1 if some query had more than
  * ~900 points inside its error band (result then incomplete: use mub_knn_l2_f32), bit2 on an internal timeout. */
-size_t mub_knn_l2_tc_workspace_bytes(int64_t nq, int64_t nc);
+size_t mub_knn_l2_tc_workspace_bytes(int64_t nq, int64_t nc, int32_t d);
 int mub_knn_l2_tc_f32(const float* X, int64_t nq, const float* Y, int64_t nc, int32_t d, int32_t ld, int32_t k,
                       int32_t* out_idx, float* out_dist, void* workspace, size_t workspace_bytes, int32_t* status,
                       mub_stream_t stream);

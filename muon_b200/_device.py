@@ -516,7 +516,7 @@ def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Opti
 
     algo: "simt" (fp32 CUDA-core kernel), "tc" (tcgen05 TF32 candidate pass + fp32 re-rank, same result; falls back
     to "simt" -- another GPU kernel, not the host -- if a query has too many points inside the TF32 error band)
-    or None = $MUON_B200_KNN, default "simt"."""
+    or None = $MUON_B200_KNN, default "tc"."""
     require_cuda()
     Y = X if Y is None else Y
     assert X.dtype == torch.float32 and Y.dtype == torch.float32 and X.is_contiguous() and Y.is_contiguous()
@@ -524,9 +524,9 @@ def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Opti
     nq, d = X.shape
     idx = torch.empty((nq, k), dtype=torch.int32, device=X.device)
     dist = torch.empty((nq, k), dtype=torch.float32, device=X.device)
-    algo = os.environ.get("MUON_B200_KNN", "simt") if algo is None else algo
+    algo = os.environ.get("MUON_B200_KNN", "tc") if algo is None else algo
     if algo == "tc" and d <= 128 and k <= 512:
-        nbytes = int(load().mub_knn_l2_tc_workspace_bytes(nq, Y.shape[0]))
+        nbytes = int(load().mub_knn_l2_tc_workspace_bytes(nq, Y.shape[0], d))
         ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=X.device)
         status = torch.zeros(1, dtype=torch.int32, device=X.device)
         call("mub_knn_l2_tc_f32", ptr(X), nq, ptr(Y), Y.shape[0], d, d, k, ptr(idx), ptr(dist), ptr(ws), nbytes,

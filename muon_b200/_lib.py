@@ -53,7 +53,7 @@ SPECIAL_RESTYPE = {
     "mub_last_error": ([], C.c_char_p),
     "mub_gram_workspace_bytes": ([i64, i32], C.c_size_t),
     "mub_wnn_bandwidth_workspace_bytes": ([i32, i32], C.c_size_t),
-    "mub_knn_l2_tc_workspace_bytes": ([i64, i64], C.c_size_t),
+    "mub_knn_l2_tc_workspace_bytes": ([i64, i64, i32], C.c_size_t),
 }
 
 TFIDF_LOG_TF, TFIDF_LOG_IDF, TFIDF_LOG_TFIDF, TFIDF_NO_SCALE, TFIDF_BINARIZE = 1, 2, 4, 8, 16

@@ -20,8 +20,10 @@
 //           same arithmetic as knn.cu (sequential fmaf over the dimensions), k rounds of (distance, index) minimum
 //           extraction.
 //
-// First version: single-stage (load -> MMA -> epilogue in sequence; two CTAs per SM overlap each other), plain
-// global->shared copies instead of TMA.  Every mbarrier wait is bounded; a timeout is reported through `status`.
+// Operands are packed once per call (knn_tc_pack_kernel) into per-tile blocks that already have the shared-memory
+// layout, so that staging a tile is one contiguous, fully coalesced copy (and can become a single 1-D TMA bulk copy).
+// First version: single-stage (load -> MMA -> epilogue in sequence; the CTAs co-resident on an SM overlap each
+// other), plain global->shared copies.  Every mbarrier wait is bounded; a timeout is reported through `status`.
 #include <float.h>
 #include <math.h>
 
@@ -55,32 +57,65 @@ __device__ __forceinline__ float tc_from_okey(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-__global__ void knn_tc_norms_kernel(const float* __restrict__ X, int64_t n, int d, int ld, float* __restrict__ norms,
-                                    unsigned int* __restrict__ maxbits) {
+// Pack X[n x ld] into 128-row tiles in the canonical UMMA K-major layout: float4 index (tile*chunks + c)*128 + r holds
+// dims 4c..4c+3 of row tile*128+r (zero beyond d and beyond n); also |x|^2 (sequential fmaf) and its maximum.
+__global__ void knn_tc_pack_kernel(const float* __restrict__ X, int64_t n, int d, int ld, int Kp, float4* __restrict__ pk,
+                                   float* __restrict__ norms, unsigned int* __restrict__ maxbits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t n_pad = (n + kTcM - 1) / kTcM * kTcM;
+    if (i >= n_pad) return;
+    const int64_t tile = i / kTcM;
+    const int r = (int)(i % kTcM);
+    const int chunks = Kp / 4;
+    const bool live = i < n;
     float s = 0.f;
-    for (int t = 0; t < d; ++t) {
-        const float v = X[(size_t)i * ld + t];
-        s = fmaf(v, v, s);
+    for (int c = 0; c < chunks; ++c) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int dim = c * 4 + e;
+            v[e] = (live && dim < d) ? X[(size_t)i * ld + dim] : 0.f;
+            s = fmaf(v[e], v[e], s);
+        }
+        pk[((size_t)tile * chunks + c) * kTcM + r] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    norms[i] = s;
-    if (maxbits) atomicMax(maxbits, __float_as_uint(s));   // s >= 0: the bit pattern is monotone
+    if (live) {
+        norms[i] = s;
+        if (maxbits) atomicMax(maxbits, __float_as_uint(s));   // s >= 0: the bit pattern is monotone
+    }
 }
 
 // Re-derive tau from the buffer (k-th smallest key, rounded up to a 2^12-ulp bucket, plus the slack) and drop the
-// entries above it.  Called warp-wide; every lane works on its own column of the [cap][128] buffers.
-__device__ __forceinline__ void tc_compact(float* __restrict__ kb, int32_t* __restrict__ ib, int tid, int k, float slack,
-                                           int& cnt, float& tau) {
+// entries above it.  Called warp-wide; every lane works on its own column of the [cap][128] buffers and of the
+// [16][128] shared-memory histogram `hist` (radix select on the 20-bit key prefix, 4 bits per pass).
+__device__ __forceinline__ void tc_compact(float* __restrict__ kb, int32_t* __restrict__ ib, int32_t* __restrict__ hist,
+                                           int tid, int k, float slack, int& cnt, float& tau) {
     if (cnt >= k) {
-        uint32_t lo = 0, hi = 0xFFFFFu;
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            int c = 0;
-            for (int i = 0; i < cnt; ++i) c += ((tc_okey(kb[(size_t)i * kTcM + tid]) >> 12) <= mid) ? 1 : 0;
-            if (c >= k) hi = mid; else lo = mid + 1;
+        uint32_t H = 0;          // high digits of the k-th smallest prefix found so far
+        int below = 0;           // entries whose prefix is below every prefix starting with H
+#pragma unroll 1
+        for (int s = 16; s >= 0; s -= 4) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hist[j * kTcM + tid] = 0;
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const uint32_t p = tc_okey(kb[(size_t)i * kTcM + tid]) >> 12;
+                if ((p >> (s + 4)) == H) hist[((p >> s) & 15u) * kTcM + tid] += 1;
+            }
+            int acc = below, D = 15;
+            bool found = false;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int hj = hist[j * kTcM + tid];
+                if (!found) {
+                    if (acc + hj >= k) { D = j; found = true; }
+                    else acc += hj;
+                }
+            }
+            below = acc;
+            H = (H << 4) | (uint32_t)D;
         }
-        float base = tc_from_okey((lo << 12) | 0xFFFu);   // upper end of the bucket holding the k-th smallest key
+        float base = tc_from_okey((H << 12) | 0xFFFu);    // upper end of the bucket holding the k-th smallest key
         if (!(base <= FLT_MAX)) base = FLT_MAX;            // bucket top beyond the finite range (or NaN pattern)
         tau = base + slack;
         int w = 0;
@@ -98,8 +133,8 @@ __device__ __forceinline__ void tc_compact(float* __restrict__ kb, int32_t* __re
 }
 
 __global__ void __launch_bounds__(kTcThreads)
-knn_tc_candidates_kernel(const float* __restrict__ X, const float* __restrict__ xnorm, int64_t nq,
-                         const float* __restrict__ Y, const float* __restrict__ ynorm, int64_t nc, int d, int ld, int Kp,
+knn_tc_candidates_kernel(const float4* __restrict__ Xpk, const float* __restrict__ xnorm, int64_t nq,
+                         const float4* __restrict__ Ypk, const float* __restrict__ ynorm, int64_t nc, int Kp,
                          int k, const unsigned int* __restrict__ ymax_bits, float* __restrict__ kbuf,
                          int32_t* __restrict__ ibuf, int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt,
                          int32_t* __restrict__ status) {
@@ -111,6 +146,7 @@ knn_tc_candidates_kernel(const float* __restrict__ X, const float* __restrict__ 
     unsigned char* sQ = smem;                                   // [chunks][128][16 B]
     unsigned char* sC = smem + (size_t)chunks * kTcM * 16;      // [chunks][128][16 B]
     float* sCn = reinterpret_cast<float*>(sC + (size_t)chunks * kTcN * 16);   // [2][128] candidate norms
+    int32_t* hist = reinterpret_cast<int32_t*>(sCn + 2 * kTcN);               // [16][128] radix-select counters
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(&tmem_base_s)), "r"(kTcN));
@@ -141,14 +177,11 @@ knn_tc_candidates_kernel(const float* __restrict__ X, const float* __restrict__ 
     for (int64_t qt = blockIdx.x; qt < n_qt && !dead; qt += gridDim.x) {
         const int64_t row = qt * kTcM + tid;
         const bool live = row < nq;
-        for (int c = 0; c < chunks; ++c) {
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int dim = c * 4 + e;
-                v[e] = (live && dim < d) ? __ldg(X + (size_t)row * ld + dim) : 0.f;
-            }
-            *reinterpret_cast<float4*>(sQ + ((size_t)c * kTcM + tid) * 16) = make_float4(v[0], v[1], v[2], v[3]);
+        {   // the packed tile already has the shared-memory layout: contiguous copy
+            const float4* src = Xpk + (size_t)qt * chunks * kTcM;
+            float4* dst = reinterpret_cast<float4*>(sQ);
+#pragma unroll 4
+            for (int i = tid; i < chunks * kTcM; i += kTcThreads) dst[i] = __ldg(src + i);
         }
         const float qn = live ? xnorm[row] : 0.f;
         // 2 x (error bound of a() = 2^-8 |q| max|c|), doubled again for safety, plus fp32 rounding of the norms
@@ -159,7 +192,7 @@ knn_tc_candidates_kernel(const float* __restrict__ X, const float* __restrict__ 
 
         for (int64_t c0 = 0; c0 < nc; c0 += kTcN, ++it) {
             if (__any_sync(0xffffffffu, cnt > kTcCap - kTcN)) {
-                tc_compact(kb, ib, tid, k, slack, cnt, tau);
+                tc_compact(kb, ib, hist, tid, k, slack, cnt, tau);
                 if (cnt > kTcCap - kTcN) {                      // more than 896 candidates inside the slack band
                     overflow = 1;
                     cnt = kTcCap - kTcN;
@@ -167,14 +200,11 @@ knn_tc_candidates_kernel(const float* __restrict__ X, const float* __restrict__ 
             }
             const int64_t crow = c0 + tid;
             const bool cl = crow < nc;
-            for (int c = 0; c < chunks; ++c) {
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int dim = c * 4 + e;
-                    v[e] = (cl && dim < d) ? __ldg(Y + (size_t)crow * ld + dim) : 0.f;
-                }
-                *reinterpret_cast<float4*>(sC + ((size_t)c * kTcN + tid) * 16) = make_float4(v[0], v[1], v[2], v[3]);
+            {
+                const float4* src = Ypk + (size_t)(c0 / kTcN) * chunks * kTcN;
+                float4* dst = reinterpret_cast<float4*>(sC);
+#pragma unroll 4
+                for (int i = tid; i < chunks * kTcN; i += kTcThreads) dst[i] = __ldg(src + i);
             }
             float* cn = sCn + (it & 1) * kTcN;
             cn[tid] = cl ? ynorm[crow] : INFINITY;
@@ -236,7 +266,7 @@ knn_tc_candidates_kernel(const float* __restrict__ X, const float* __restrict__ 
             }
         }
         if (dead) break;
-        tc_compact(kb, ib, tid, k, slack, cnt, tau);            // final trim
+        tc_compact(kb, ib, hist, tid, k, slack, cnt, tau);      // final trim
         if (live) {
             cand_cnt[row] = cnt;
             for (int i = 0; i < cnt; ++i) cand[(size_t)row * kTcCap + i] = ib[(size_t)i * kTcM + tid];
@@ -309,11 +339,11 @@ knn_tc_rerank_kernel(const float* __restrict__ X, int64_t nq, const float* __res
 }
 
 struct TcLayout {
-    size_t xnorm, ynorm, ymax, cnt, cand, kbuf, ibuf, total;
-    int grid;
+    size_t xnorm, ynorm, ymax, cnt, cand, kbuf, ibuf, xpk, ypk, total;
+    int grid, Kp;
 };
 
-static TcLayout tc_layout(int64_t nq, int64_t nc) {
+static TcLayout tc_layout(int64_t nq, int64_t nc, int d) {
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     TcLayout L;
     const int64_t n_qt = (nq + kTcM - 1) / kTcM;
@@ -328,6 +358,9 @@ static TcLayout tc_layout(int64_t nq, int64_t nc) {
     L.cand = o;  o = up(o + sizeof(int32_t) * (size_t)nq * kTcCap);
     L.kbuf = o;  o = up(o + sizeof(float) * (size_t)g * kTcCap * kTcM);
     L.ibuf = o;  o = up(o + sizeof(int32_t) * (size_t)g * kTcCap * kTcM);
+    L.Kp = (d + 7) / 8 * 8;
+    L.xpk = o;   o = up(o + sizeof(float) * (size_t)((nq + kTcM - 1) / kTcM) * kTcM * L.Kp);
+    L.ypk = o;   o = up(o + sizeof(float) * (size_t)((nc + kTcN - 1) / kTcN) * kTcN * L.Kp);
     L.total = o;
     return L;
 }
@@ -336,9 +369,9 @@ static TcLayout tc_layout(int64_t nq, int64_t nc) {
 
 extern "C" {
 
-size_t mub_knn_l2_tc_workspace_bytes(int64_t nq, int64_t nc) {
-    if (nq < 0 || nc < 0) return 0;
-    return mub::tc_layout(nq, nc).total;
+size_t mub_knn_l2_tc_workspace_bytes(int64_t nq, int64_t nc, int32_t d) {
+    if (nq < 0 || nc < 0 || d < 1 || d > 128) return 0;
+    return mub::tc_layout(nq, nc, d).total;
 }
 
 int mub_knn_l2_tc_f32(const float* X, int64_t nq, const float* Y, int64_t nc, int32_t d, int32_t ld, int32_t k,
@@ -350,7 +383,7 @@ int mub_knn_l2_tc_f32(const float* X, int64_t nq, const float* Y, int64_t nc, in
     MUB_REQUIRE(nc < (int64_t)1 << 31, "knn_l2_tc: more than 2^31 candidates");
     if (nq == 0) return 0;
     MUB_REQUIRE(X && Y && out_idx && out_dist && workspace && status, "knn_l2_tc: null pointer");
-    const mub::TcLayout L = mub::tc_layout(nq, nc);
+    const mub::TcLayout L = mub::tc_layout(nq, nc, d);
     MUB_REQUIRE(workspace_bytes >= L.total, "knn_l2_tc: workspace of %zu B, need %zu B", workspace_bytes, L.total);
     cudaStream_t s = (cudaStream_t)stream;
     unsigned char* ws = (unsigned char*)workspace;
@@ -366,17 +399,21 @@ int mub_knn_l2_tc_f32(const float* X, int64_t nq, const float* Y, int64_t nc, in
         mub::set_error("knn_l2_tc: memset: %s", cudaGetErrorString(e));
         return -2;
     }
-    mub::knn_tc_norms_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, s>>>(X, nq, d, ld, xnorm, nullptr);
-    if (nc > 0) mub::knn_tc_norms_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(Y, nc, d, ld, ynorm, ymax);
-    const int Kp = (d + 7) / 8 * 8;
-    const size_t smem = (size_t)(Kp / 4) * (mub::kTcM + mub::kTcN) * 16 + 2 * mub::kTcN * sizeof(float);
+    float4* xpk = (float4*)(ws + L.xpk);
+    float4* ypk = (float4*)(ws + L.ypk);
+    const int Kp = L.Kp;
+    const int64_t nq_pad = (nq + mub::kTcM - 1) / mub::kTcM * mub::kTcM, nc_pad = (nc + mub::kTcN - 1) / mub::kTcN * mub::kTcN;
+    mub::knn_tc_pack_kernel<<<(unsigned)(nq_pad / 128), 128, 0, s>>>(X, nq, d, ld, Kp, xpk, xnorm, nullptr);
+    if (nc > 0) mub::knn_tc_pack_kernel<<<(unsigned)(nc_pad / 128), 128, 0, s>>>(Y, nc, d, ld, Kp, ypk, ynorm, ymax);
+    const size_t smem = (size_t)(Kp / 4) * (mub::kTcM + mub::kTcN) * 16 + 2 * mub::kTcN * sizeof(float) +
+                        16 * mub::kTcM * sizeof(int32_t);
     e = cudaFuncSetAttribute(mub::knn_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         mub::set_error("knn_l2_tc: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
         return -2;
     }
-    mub::knn_tc_candidates_kernel<<<L.grid, mub::kTcThreads, smem, s>>>(X, xnorm, nq, Y, ynorm, nc, d, ld, Kp, k, ymax, kbuf,
-                                                                         ibuf, cand, cnt, status);
+    mub::knn_tc_candidates_kernel<<<L.grid, mub::kTcThreads, smem, s>>>(xpk, xnorm, nq, ypk, ynorm, nc, Kp, k, ymax, kbuf, ibuf,
+                                                                         cand, cnt, status);
     int rc = mub::check_launch("knn_l2_tc candidates");
     if (rc) return rc;
     mub::knn_tc_rerank_kernel<<<(unsigned)((nq + mub::kTcRerankWarps - 1) / mub::kTcRerankWarps), mub::kTcRerankWarps * 32, 0, s>>>(

@@ -73,7 +73,7 @@ def test_tensor_core_knn_is_bit_identical_to_the_simt_kernel(cuda, nq, nc, d, k,
     # call the C ABI directly so that a fallback inside knn_l2 cannot mask a failure
     idx = torch.empty((nq, k), dtype=torch.int32, device="cuda")
     dist = torch.empty((nq, k), dtype=torch.float32, device="cuda")
-    nbytes = int(load().mub_knn_l2_tc_workspace_bytes(nq, nc))
+    nbytes = int(load().mub_knn_l2_tc_workspace_bytes(nq, nc, d))
     ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
     call("mub_knn_l2_tc_f32", ptr(X), nq, ptr(Y), nc, d, d, k, ptr(idx), ptr(dist), ptr(ws), nbytes, ptr(status), stream_ptr())
