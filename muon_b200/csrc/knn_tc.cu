@@ -11,8 +11,10 @@
 //           ceil(d/8) tcgen05.mma.kind::tf32 instructions that accumulate S = Q C^T in 128 TMEM columns and commits
 //           to an mbarrier; the 128 threads then read their own row of S with tcgen05.ld (thread t = TMEM lane t),
 //           form a(q,c) = |c|^2 - 2 S and keep every candidate with a <= tau_q in a per-query buffer.
-//           TF32 truncates the inputs to 10 mantissa bits, so a() carries an error of at most 2^-8 |q||c|; the
-//           threshold is therefore tau_q = (k-th smallest a seen so far, rounded up) + 2 * bound.  Order statistics
+//           TF32 truncates the inputs to 10 mantissa bits, so a() carries an error of at most 2^-8 |q||c| -- too
+//           coarse for concentrated distance distributions, so for d <= 64 the operands are split 3xTF32
+//           (big + small parts along a tripled K axis, see knn_tc_pack_kernel) and the error drops to ~5e-5 |q||c|.
+//           The threshold is tau_q = (k-th smallest a seen so far, rounded up) + 2 * bound.  Order statistics
 //           move by at most the perturbation, hence no true k-nearest neighbour is ever rejected.
 //           When a buffer fills up (1024 entries) the warp re-derives tau by bisection on the float keys and drops
 //           what no longer qualifies.
@@ -57,27 +59,43 @@ __device__ __forceinline__ float tc_from_okey(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
-// Pack X[n x ld] into 128-row tiles in the canonical UMMA K-major layout: float4 index (tile*chunks + c)*128 + r holds
-// dims 4c..4c+3 of row tile*128+r (zero beyond d and beyond n); also |x|^2 (sequential fmaf) and its maximum.
-__global__ void knn_tc_pack_kernel(const float* __restrict__ X, int64_t n, int d, int ld, int Kp, float4* __restrict__ pk,
-                                   float* __restrict__ norms, unsigned int* __restrict__ maxbits) {
+// Pack X[n x ld] into 128-row tiles in the canonical UMMA K-major layout: float4 index (tile*chunks_total + c)*128 + r
+// holds 4 consecutive K values of row tile*128+r (zero beyond d and beyond n); also |x|^2 (sequential fmaf) and its
+// maximum.  split = 0: K = the Kp padded dimensions.  split = 1 / 2 (query / candidate side): 3xTF32 -- every value
+// is written as big = x truncated to TF32 (exactly representable, so the tensor core's own truncation is a no-op) and
+// small = x - big (exact in fp32); the K axis is [big | big | small] for queries and [big | small | big] for
+// candidates, so that one K = 3 Kp product gives qb.cb + qb.cs + qs.cb = q.c up to ~3 * 2^-20 |q||c|.
+__global__ void knn_tc_pack_kernel(const float* __restrict__ X, int64_t n, int d, int ld, int Kp, int split,
+                                   float4* __restrict__ pk, float* __restrict__ norms, unsigned int* __restrict__ maxbits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_pad = (n + kTcM - 1) / kTcM * kTcM;
     if (i >= n_pad) return;
     const int64_t tile = i / kTcM;
     const int r = (int)(i % kTcM);
     const int chunks = Kp / 4;
+    const int chunks_total = split ? 3 * chunks : chunks;
     const bool live = i < n;
     float s = 0.f;
     for (int c = 0; c < chunks; ++c) {
-        float v[4];
+        float v[4], big[4], small[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int dim = c * 4 + e;
             v[e] = (live && dim < d) ? X[(size_t)i * ld + dim] : 0.f;
             s = fmaf(v[e], v[e], s);
+            big[e] = __uint_as_float(__float_as_uint(v[e]) & 0xFFFFE000u);
+            small[e] = v[e] - big[e];
         }
-        pk[((size_t)tile * chunks + c) * kTcM + r] = make_float4(v[0], v[1], v[2], v[3]);
+        float4* dst = pk + ((size_t)tile * chunks_total + c) * kTcM + r;
+        if (!split) {
+            *dst = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            const float4 b4 = make_float4(big[0], big[1], big[2], big[3]);
+            const float4 s4 = make_float4(small[0], small[1], small[2], small[3]);
+            dst[0] = b4;
+            dst[(size_t)chunks * kTcM] = (split == 1) ? b4 : s4;
+            dst[(size_t)2 * chunks * kTcM] = (split == 1) ? s4 : b4;
+        }
     }
     if (live) {
         norms[i] = s;
@@ -135,7 +153,7 @@ __device__ __forceinline__ void tc_compact(float* __restrict__ kb, int32_t* __re
 __global__ void __launch_bounds__(kTcThreads)
 knn_tc_candidates_kernel(const float4* __restrict__ Xpk, const float* __restrict__ xnorm, int64_t nq,
                          const float4* __restrict__ Ypk, const float* __restrict__ ynorm, int64_t nc, int Kp,
-                         int k, const unsigned int* __restrict__ ymax_bits, float* __restrict__ kbuf,
+                         int k, float slack_rel, const unsigned int* __restrict__ ymax_bits, float* __restrict__ kbuf,
                          int32_t* __restrict__ ibuf, int32_t* __restrict__ cand, int32_t* __restrict__ cand_cnt,
                          int32_t* __restrict__ status) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -184,8 +202,10 @@ knn_tc_candidates_kernel(const float4* __restrict__ Xpk, const float* __restrict
             for (int i = tid; i < chunks * kTcM; i += kTcThreads) dst[i] = __ldg(src + i);
         }
         const float qn = live ? xnorm[row] : 0.f;
-        // 2 x (error bound of a() = 2^-8 |q| max|c|), doubled again for safety, plus fp32 rounding of the norms
-        const float slack = 4.f * 0.00390625f * sqrtf(qn) * cmax + 1e-5f * (qn + cmax * cmax);
+        // 2 x (error bound of a(), slack_rel/2 * |q| max|c|: see the host code) plus fp32 rounding of the norms
+        const float slack = slack_rel * sqrtf(qn) * cmax + 1e-5f * (qn + cmax * cmax);
+        // another CTA already found a query whose error band is too crowded: the caller will use the SIMT kernel
+        if (__syncthreads_or(*reinterpret_cast<volatile int32_t*>(status) & 2)) break;   // block-uniform decision
         float tau = live ? INFINITY : -INFINITY;
         int cnt = 0;
         int overflow = 0;
@@ -196,6 +216,7 @@ knn_tc_candidates_kernel(const float4* __restrict__ Xpk, const float* __restrict
                 if (cnt > kTcCap - kTcN) {                      // more than 896 candidates inside the slack band
                     overflow = 1;
                     cnt = kTcCap - kTcN;
+                    atomicOr(status, 2);
                 }
             }
             const int64_t crow = c0 + tid;
@@ -340,7 +361,7 @@ knn_tc_rerank_kernel(const float* __restrict__ X, int64_t nq, const float* __res
 
 struct TcLayout {
     size_t xnorm, ynorm, ymax, cnt, cand, kbuf, ibuf, xpk, ypk, total;
-    int grid, Kp;
+    int grid, Kp, Ktot, split;
 };
 
 static TcLayout tc_layout(int64_t nq, int64_t nc, int d) {
@@ -359,8 +380,10 @@ static TcLayout tc_layout(int64_t nq, int64_t nc, int d) {
     L.kbuf = o;  o = up(o + sizeof(float) * (size_t)g * kTcCap * kTcM);
     L.ibuf = o;  o = up(o + sizeof(int32_t) * (size_t)g * kTcCap * kTcM);
     L.Kp = (d + 7) / 8 * 8;
-    L.xpk = o;   o = up(o + sizeof(float) * (size_t)((nq + kTcM - 1) / kTcM) * kTcM * L.Kp);
-    L.ypk = o;   o = up(o + sizeof(float) * (size_t)((nc + kTcN - 1) / kTcN) * kTcN * L.Kp);
+    L.split = d <= 64 ? 1 : 0;                 // 3xTF32 operands need 3 * Kp * 1 KB of shared memory per tile pair
+    L.Ktot = L.split ? 3 * L.Kp : L.Kp;
+    L.xpk = o;   o = up(o + sizeof(float) * (size_t)((nq + kTcM - 1) / kTcM) * kTcM * L.Ktot);
+    L.ypk = o;   o = up(o + sizeof(float) * (size_t)((nc + kTcN - 1) / kTcN) * kTcN * L.Ktot);
     L.total = o;
     return L;
 }
@@ -401,19 +424,25 @@ int mub_knn_l2_tc_f32(const float* X, int64_t nq, const float* Y, int64_t nc, in
     }
     float4* xpk = (float4*)(ws + L.xpk);
     float4* ypk = (float4*)(ws + L.ypk);
-    const int Kp = L.Kp;
+    const int Kp = L.Kp, Ktot = L.Ktot;
     const int64_t nq_pad = (nq + mub::kTcM - 1) / mub::kTcM * mub::kTcM, nc_pad = (nc + mub::kTcN - 1) / mub::kTcN * mub::kTcN;
-    mub::knn_tc_pack_kernel<<<(unsigned)(nq_pad / 128), 128, 0, s>>>(X, nq, d, ld, Kp, xpk, xnorm, nullptr);
-    if (nc > 0) mub::knn_tc_pack_kernel<<<(unsigned)(nc_pad / 128), 128, 0, s>>>(Y, nc, d, ld, Kp, ypk, ynorm, ymax);
-    const size_t smem = (size_t)(Kp / 4) * (mub::kTcM + mub::kTcN) * 16 + 2 * mub::kTcN * sizeof(float) +
+    mub::knn_tc_pack_kernel<<<(unsigned)(nq_pad / 128), 128, 0, s>>>(X, nq, d, ld, Kp, L.split ? 1 : 0, xpk, xnorm, nullptr);
+    if (nc > 0)
+        mub::knn_tc_pack_kernel<<<(unsigned)(nc_pad / 128), 128, 0, s>>>(Y, nc, d, ld, Kp, L.split ? 2 : 0, ypk, ynorm, ymax);
+    // error of a() = |c|^2 - 2 S:  plain TF32 truncates both inputs to 10 mantissa bits -> |dS| <= 2^-9 |q||c|, so
+    // |da| <= 2^-8 |q||c|; 3xTF32 leaves ~3 * 2^-20 from the dropped/truncated small parts plus the fp32 accumulation of
+    // K <= 192 terms (<= 2^-23 each) -> |da| <= 4.6e-5 |q||c|.  tau needs twice the bound; the plain variant doubles it
+    // once more for safety.
+    const float slack_rel = L.split ? 1.2e-4f : 4.f * 0.00390625f;
+    const size_t smem = (size_t)(Ktot / 4) * (mub::kTcM + mub::kTcN) * 16 + 2 * mub::kTcN * sizeof(float) +
                         16 * mub::kTcM * sizeof(int32_t);
     e = cudaFuncSetAttribute(mub::knn_tc_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         mub::set_error("knn_l2_tc: %zu B of shared memory: %s", smem, cudaGetErrorString(e));
         return -2;
     }
-    mub::knn_tc_candidates_kernel<<<L.grid, mub::kTcThreads, smem, s>>>(xpk, xnorm, nq, ypk, ynorm, nc, Kp, k, ymax, kbuf, ibuf,
-                                                                         cand, cnt, status);
+    mub::knn_tc_candidates_kernel<<<L.grid, mub::kTcThreads, smem, s>>>(xpk, xnorm, nq, ypk, ynorm, nc, Ktot, k, slack_rel, ymax,
+                                                                         kbuf, ibuf, cand, cnt, status);
     int rc = mub::check_launch("knn_l2_tc candidates");
     if (rc) return rc;
     mub::knn_tc_rerank_kernel<<<(unsigned)((nq + mub::kTcRerankWarps - 1) / mub::kTcRerankWarps), mub::kTcRerankWarps * 32, 0, s>>>(
