@@ -167,3 +167,29 @@ def test_bench_onchip_roofline_arithmetic():
     assert abs(r["peak"] - 148 * 128 * 1.92e9 / 1e12) < 1e-9 and r["bytes_per_nnz"] == 264.0
     assert abs(r["achieved"] - 6e9 * 264 / 0.088 / 1e12) < 1e-9 and 0.45 < r["frac"] < 0.55
     assert bench.onchip_roofline(1, 64, float("nan"), 1900.0) is None and bench.onchip_roofline(1, 64, 1.0, None) is None
+
+
+def test_neighbors_argument_errors_and_no_cpu_fallback():
+    """muon/_core/preproc.py:264-398 checks, raised before any device work; without a GPU the call must fail
+    loudly instead of computing anything on the host."""
+    with pytest.raises(TypeError):
+        mu.pp.neighbors(np.ones((3, 3)))
+    ads = {}
+    for name in ("a", "b"):
+        ad = SimpleAnnData(np.zeros((6, 2)))
+        ad.obsm["X_e"] = np.random.default_rng(0).normal(size=(6, 3))
+        ad.obsp["distances"] = sp.csr_matrix(np.ones((6, 6)) - np.eye(6))
+        ad.uns["neighbors"] = {"params": {"n_neighbors": 3, "use_rep": "X_e"}, "distances_key": "distances"}
+        ads[name] = ad
+    md = SimpleMuData(ads)
+    with pytest.raises(NotImplementedError):
+        mu.pp.neighbors(md, metric="cosine")
+    del md.mod["b"].uns["neighbors"]
+    with pytest.raises(ValueError):
+        mu.pp.neighbors(md)
+    if not torch.cuda.is_available():
+        from muon_b200._lib import MuonB200Error
+        with pytest.raises(MuonB200Error):
+            mu.pp.neighbors(SimpleMuData({k: v for k, v in ads.items() if k == "a"}))
+        with pytest.raises(MuonB200Error):
+            mu.tl.mofa(SimpleMuData({"y": SimpleAnnData(np.random.default_rng(1).normal(size=(20, 8)))}), n_factors=2)
