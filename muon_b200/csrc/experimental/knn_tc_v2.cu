@@ -8,7 +8,9 @@
 //   * candidate tiles are 64 points (N = 64), pre-packed like v1, fetched by ONE 1-D TMA bulk copy each
 //     (cp.async.bulk + mbarrier complete_tx, the pattern verified in spmm_panel.cu) into a 2-stage ring;
 //   * two TMEM accumulator buffers: tcgen05.mma of tile t runs while the 128 threads filter tile t-1;
-//   * every CTA starts its sweep over the candidate tiles at a different offset (no lockstep L2 hot spot).
+//   * every CTA starts its sweep over the candidate tiles at a different offset (no lockstep L2 hot spot);
+//   * (added after the first hardware run showed v2 == v1 in time) the candidate-buffer compaction issues its
+//     global loads in batches of 8 (v2_compact) -- NOT YET RUN ON HARDWARE.
 // This file is a stand-alone harness: it compiles v1 (by including ../knn_tc.cu) and v2 into one binary, runs both on
 // the same synthetic points and reports time and whether the final neighbour lists are identical.
 //
@@ -79,6 +81,69 @@ __global__ void v2_pack_kernel(const float* __restrict__ X, int64_t n, int d, in
             dst[(size_t)2 * chunks * R] = (split == 1) ? s4 : b4;
         }
     }
+}
+
+// tc_compact with the buffer loads batched: 8 independent L2 loads are issued before the first histogram update, so a
+// pass costs ~cnt/8 memory round trips instead of ~cnt (the measured limiter of v1).
+__device__ __forceinline__ void v2_compact(float* __restrict__ kb, int32_t* __restrict__ ib, int32_t* __restrict__ hist,
+                                           int tid, int k, float slack, int& cnt, float& tau) {
+    if (cnt < k) return;
+    uint32_t H = 0;
+    int below = 0;
+#pragma unroll 1
+    for (int s = 16; s >= 0; s -= 4) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hist[j * kTcM + tid] = 0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < cnt; i0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (i0 + u < cnt) ? __ldcg(kb + (size_t)(i0 + u) * kTcM + tid) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (i0 + u < cnt) {
+                    const uint32_t p = tc_okey(v[u]) >> 12;
+                    if ((p >> (s + 4)) == H) hist[((p >> s) & 15u) * kTcM + tid] += 1;
+                }
+            }
+        }
+        int acc = below, D = 15;
+        bool found = false;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int hj = hist[j * kTcM + tid];
+            if (!found) {
+                if (acc + hj >= k) { D = j; found = true; }
+                else acc += hj;
+            }
+        }
+        below = acc;
+        H = (H << 4) | (uint32_t)D;
+    }
+    float base = tc_from_okey((H << 12) | 0xFFFu);
+    if (!(base <= FLT_MAX)) base = FLT_MAX;
+    tau = base + slack;
+    int w = 0;
+#pragma unroll 1
+    for (int i0 = 0; i0 < cnt; i0 += 8) {
+        float v[8];
+        int32_t jj[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool in = i0 + u < cnt;
+            v[u] = in ? __ldcg(kb + (size_t)(i0 + u) * kTcM + tid) : INFINITY;
+            jj[u] = in ? __ldcg(ib + (size_t)(i0 + u) * kTcM + tid) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (i0 + u < cnt && v[u] <= tau) {                  // w <= i0 + u: never overwrites an unread entry
+                kb[(size_t)w * kTcM + tid] = v[u];
+                ib[(size_t)w * kTcM + tid] = jj[u];
+                ++w;
+            }
+        }
+    }
+    cnt = w;
 }
 
 // filter one 128 x 64 accumulator buffer (thread = TMEM lane = query)
@@ -237,7 +302,7 @@ knn_tc_candidates_v2_kernel(const float4* __restrict__ Xpk, const float* __restr
             if (t >= 1) {                                             // filter tile t-1 while the MMAs of tile t run
                 const uint32_t pit = it - 1;
                 if (__any_sync(0xffffffffu, cnt > kTcCap - kV2N)) {
-                    tc_compact(kb, ib, hist, tid, k, slack, cnt, tau);
+                    v2_compact(kb, ib, hist, tid, k, slack, cnt, tau);
                     if (cnt > kTcCap - kV2N) {
                         overflow = 1;
                         cnt = kTcCap - kV2N;
@@ -251,7 +316,7 @@ knn_tc_candidates_v2_kernel(const float4* __restrict__ Xpk, const float* __restr
             if (t < T) ++it;
         }
         if (dead) break;
-        tc_compact(kb, ib, hist, tid, k, slack, cnt, tau);
+        v2_compact(kb, ib, hist, tid, k, slack, cnt, tau);
         if (live) {
             cand_cnt[row] = cnt;
             for (int i = 0; i < cnt; ++i) cand[(size_t)row * kTcCap + i] = ib[(size_t)i * kTcM + tid];
