@@ -1,4 +1,6 @@
-// EXPERIMENTAL, NOT PART OF libmuon_b200.so, NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent).
+// EXPERIMENTAL, NOT PART OF libmuon_b200.so.  The pipeline below ran once on a B200 at the very end of round 1
+// (profiles/knn_tc_v1_vs_v2_100k.json: output bit-identical to v1, same time); the batched compaction added afterwards
+// (v2_compact) has not run on hardware yet.
 //
 // Round-2 candidate for the tensor-core kNN candidate pass (knn_tc.cu: knn_tc_candidates_kernel, v1).  v1 is correct
 // and bit-identical to the SIMT kernel but spends ~58 k cycles per 128 x 128 tile where MMA + epilogue need ~3 k:
