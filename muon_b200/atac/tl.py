@@ -60,22 +60,20 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
              "(clustered singular values around the k-th component?); the leading components are still accurate")
 
     # post-processing of tools.py:60-65 on the device (moments allreduced over cell shards)
-    _ph = phase("lsi.post_and_d2h")
-    _ph.__enter__()
-    emb = U
-    if scale_embeddings:
-        mom = torch.stack([U.sum(0, dtype=torch.float64), (U.to(torch.float64) ** 2).sum(0)])
-        _dist.all_reduce_sum_(mom)
-        mean = mom[0] / n_total
-        std = (mom[1] / n_total - mean**2).clamp_min(0).sqrt()     # numpy std, ddof=0
-        emb = ((U.to(torch.float64) - mean) / std).to(torch.float32)
-    stdev = s / np.sqrt(n_total - 1)
+    with phase("lsi.post_and_d2h"):
+        emb = U
+        if scale_embeddings:
+            mom = torch.stack([U.sum(0, dtype=torch.float64), (U.to(torch.float64) ** 2).sum(0)])
+            _dist.all_reduce_sum_(mom)
+            mean = mom[0] / n_total
+            std = (mom[1] / n_total - mean**2).clamp_min(0).sqrt()     # numpy std, ddof=0
+            emb = ((U.to(torch.float64) - mean) / std).to(torch.float32)
+        stdev = s / np.sqrt(n_total - 1)
 
-    out_dtype = np.float32 if resident or X.dtype == np.float32 else np.float64
-    adata.obsm["X_lsi"] = _device.to_host(emb.contiguous()).astype(out_dtype, copy=False)
-    adata.uns["lsi"] = {"stdev": stdev.cpu().numpy().astype(out_dtype, copy=False)}
-    adata.varm["LSI"] = _device.to_host(V.contiguous()).astype(out_dtype, copy=False)
-    _ph.__exit__(None, None, None)
+        out_dtype = np.float32 if resident or X.dtype == np.float32 else np.float64
+        adata.obsm["X_lsi"] = _device.to_host(emb.contiguous()).astype(out_dtype, copy=False)
+        adata.uns["lsi"] = {"stdev": stdev.cpu().numpy().astype(out_dtype, copy=False)}
+        adata.varm["LSI"] = _device.to_host(V.contiguous()).astype(out_dtype, copy=False)
     if return_info:
         return info
     return None
