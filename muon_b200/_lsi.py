@@ -161,12 +161,19 @@ def _orth_against(W: torch.Tensor, Q: torch.Tensor, passes: int = 2):
 
 
 def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optional[int] = None,
-                  max_restarts: int = 4, seed: int = 0, verbose: bool = False):
+                  max_restarts: int = 4, seed: int = 0, verbose: bool = False, polish: Optional[bool] = None):
     """Top-k singular triplets of the (cell-sharded) matrix behind ``op``.
 
     Returns (U [n_local x k] fp32, s [k] fp64, V [d x k] fp32, SvdInfo).  ``pad_to`` is the padded
     dense width the kernels run at (32/64/128); the Krylov block size is min(pad_to, d).
+
+    ``polish`` (default: $MUON_B200_LSI_POLISH, "1"): finish with scipy's Rayleigh-Ritz tail (one more pass over A).
+    ``False`` returns the Ritz triplets of the Krylov spaces themselves -- U_k from the stored left blocks -- and
+    saves that pass; on the CPU driver tests both are equally accurate (sigma 1e-7, vectors < 1e-6), the GPU parity
+    suite has only been run with the polish so far, hence the default.
     """
+    if polish is None:
+        polish = os.environ.get("MUON_B200_LSI_POLISH", "1") != "0"
     d, dev, P = op.d, op.device, pad_to
     k = int(k)
     b = min(P, d, getattr(op, "n_total", d))
@@ -192,6 +199,7 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
         U, R = _cholqr2(op, Y, b)              # U: n x P (cols >= b are zero)
         Bmat[:b, :b] = R
         blocks = [(0, b)]                      # column ranges of the blocks
+        Ublocks = None if polish else [U[:, :b].clone()]   # left Lanczos blocks (only needed without the polish)
         prev_res, stagn = None, 0
         done = False
         while True:
@@ -248,6 +256,10 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
                 with phase("lsi.ritz_vectors"):
                     Vk = Vall[:, :m] @ Zt[:kk, :].T.to(torch.float32)      # d x k right Ritz vectors
                     V0_next = Vall[:, :m] @ Zt[:b, :].T.to(torch.float32)
+                    if Ublocks is not None:                                # left Ritz vectors: U_all (B Z / sigma)
+                        Xl = (Bm @ Zt[:kk, :].T) / sig[:kk].clamp_min(1e-300)
+                        Uk_lanczos = torch.cat(Ublocks, 1) @ Xl.to(torch.float32)
+                        s_lanczos = sig[:kk].clone()
                 break
             # ---- left side: Y = A V_{j+1} - U_j S_j^T, CholeskyQR2 --------------------------
             Sj_use = Sj[:bn, :]                                    # if the block shrank keep bn rows
@@ -262,6 +274,8 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
             Bmat[j0:j1, m:m + bn] = Sj_use.T
             Bmat[m:m + bn, m:m + bn] = Rn
             blocks.append((m, m + bn))
+            if Ublocks is not None:
+                Ublocks.append(U[:, :bn].clone())
             m += bn
         info.basis = m
         info.converged = (rmax <= tol) or m >= d
@@ -271,6 +285,8 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
         info.restarts += 1
         V0, _ = torch.linalg.qr(V0_next)
 
+    if not polish:
+        return Uk_lanczos, s_lanczos, Vk, info
     # ---- final Rayleigh-Ritz polish, as scipy does after ARPACK (_svds.py:508-533) -------------
     with phase("lsi.final"):
         Vk, _ = _qr_dspace(op, Vk, P)

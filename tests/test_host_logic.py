@@ -89,6 +89,12 @@ def test_block_lanczos_matches_svds(k, P):
     assert info.converged
     out = compare_lsi({"svalues": s.numpy(), "U": U.numpy(), "LSI": V.numpy()}, ref, rtol=1e-4, s_next=s_next)
     assert out["sigma_rel"] < 1e-5
+    # without the final Rayleigh-Ritz pass (opt-in): same accuracy from the Krylov spaces alone, one pass fewer
+    U2, s2, V2, info2 = truncated_svd(ScipyOperator(X), k, P, tol=1e-5, polish=False)
+    assert info2.passes == info.passes - 1 and U2.shape == U.shape
+    out2 = compare_lsi({"svalues": s2.numpy(), "U": U2.numpy(), "LSI": V2.numpy()}, ref, rtol=1e-4, s_next=s_next)
+    assert out2["sigma_rel"] < 1e-5
+    assert np.abs(U2.numpy().T.astype(np.float64) @ U2.numpy() - np.eye(k)).max() < 1e-5
 
 
 def test_block_lanczos_small_dims_and_restart():
