@@ -203,6 +203,44 @@ int mub_wnn_affinity_topk_f32(int32_t n_mod, const float* const* reps, const int
                               int64_t n, int32_t n_cand, int32_t n_out, int32_t* out_idx, double* out_dist,
                               int32_t* status, mub_stream_t stream);
 
+/* ---- half-precision dense operand for the early block-Lanczos steps of the svds replacement --------------
+ * (scipy _svds.py:428-460 as driven from muon/_atac/tools.py:53).  The operator application is bound by the
+ * 4*ld bytes of the dense operand every non-zero pulls through L2 -> L1; with B stored as IEEE half that is
+ * 2*ld.  Products and sums stay fp32.  f32_to_f16_scaled: dst[i] = half(src[i] * scale), n a multiple of 4
+ * (scale: a power of two that lifts orthonormal columns, |x| <= 1, out of the subnormal range).
+ * spmm_csr_h16 / spmm_csrp_h16: C (=|+=) out_scale * A * B_half, same rules as mub_spmm_csr_f32. */
+int mub_f32_to_f16_scaled(const float* src, int64_t n, float scale, void* dst, mub_stream_t stream);
+int mub_spmm_csr_h16(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                     int64_t n_cols, const void* B_half, int32_t ld, float* C, int32_t accumulate,
+                     float out_scale, unsigned long long* row_counter, mub_stream_t stream);
+int mub_spmm_csrp_h16(const int64_t* indptr, const int32_t* pairs, int64_t n_rows, int64_t n_cols,
+                      const void* B_half, int32_t ld, float* C, int32_t accumulate, float out_scale,
+                      unsigned long long* row_counter, mub_stream_t stream);
+
+/* ---- host <-> device staging (ingest side: adata.X is a pageable scipy CSR, muon/_atac/preproc.py:86-129
+ * reads it and rebinds a freshly allocated host matrix).  A stager owns a ring of pinned buffers and a pool
+ * of host threads; transfers are chunked through the ring so that the host-side copy of chunk i+1 overlaps
+ * the DMA of chunk i.  Fused into the host-side copy: int64 -> int32 narrowing of scipy's index arrays
+ * (nnz >= 2^31) and a position-dependent 64-bit fingerprint  sum_i (e_i + C1) * (i*C2 + C3)  of the 32-bit
+ * element stream, by which a later call can prove a host array still equals its device twin.
+ * Pointers ending in _h are HOST pointers.  A stager is not thread-safe: one transfer at a time.
+ *   create : n_bufs pinned buffers of buf_bytes each (n_bufs = 0: thread pool only, no CUDA context needed)
+ *   h2d    : src_elem_bytes 1, 4 or 8; narrow != 0 (8-byte sources): int64 -> int32, *overflow_h = 1 if a value
+ *            does not fit; hash_h (optional; 4-byte or narrowed sources) receives the fingerprint.  Chunks are
+ *            enqueued on `stream`; returns when the last chunk is enqueued.
+ *   d2h    : synchronous; hash_h (optional, n_bytes % 4 == 0) receives the fingerprint of what was written.
+ *   host_fingerprint   : fingerprint of a host array (elem_bytes 4, or 8 = int64 read as narrowed int32).
+ *   device_fingerprint : the same function of a device array of n 32-bit elements, ACCUMULATED into *out
+ *            (device uint64, zeroed by the caller). */
+int mub_stager_create(size_t buf_bytes, int32_t n_bufs, int32_t n_threads, void** out);
+int mub_stager_destroy(void* stager);
+int mub_stager_h2d(void* stager, const void* src_h, void* dst, size_t n_elems, int32_t src_elem_bytes,
+                   int32_t narrow, uint64_t* hash_h, int32_t* overflow_h, mub_stream_t stream);
+int mub_stager_d2h(void* stager, const void* src, void* dst_h, size_t n_bytes, uint64_t* hash_h,
+                   mub_stream_t stream);
+int mub_host_fingerprint(void* stager, const void* src_h, size_t n_elems, int32_t elem_bytes, uint64_t* hash_h);
+int mub_device_fingerprint(const void* src, int64_t n, uint64_t* out, mub_stream_t stream);
+
 /* ---- synthetic ATAC count generator (benchmark / test input) ---------------
  * Deterministic counter-based planted-topic model; bit-identical to the numpy generator in
  * muon_b200/_synth.py.  Step 1 writes nnz per row; caller scans into indptr; step 2 fills.

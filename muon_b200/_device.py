@@ -31,107 +31,175 @@ def pad_width(l: int) -> int:
     raise NotImplementedError(f"dense block width {l} > 128 is not supported yet")
 
 
-_STAGE_BYTES = 256 << 20
-_PINNED = []          # two cached pinned staging buffers (uint8), allocated on first large transfer
-_POOL = None          # thread pool for host-side memcpy into / out of the staging buffers
-_COPY_THREADS = 16
+# ---- host <-> device transfers: native staging engine (csrc/staging.cu) ---------------------------------
+_STAGE_BYTES = int(os.environ.get("MUON_B200_STAGE_MB", "64")) << 20
+_STAGE_BUFS = int(os.environ.get("MUON_B200_STAGE_BUFS", "4"))
+HOST_TIMES = None     # None, or dict name -> seconds of host wall time (bench.py's e2e breakdown)
 
 
-def _staging():
-    global _POOL
-    if not _PINNED:
-        _PINNED.extend(torch.empty(_STAGE_BYTES, dtype=torch.uint8).pin_memory() for _ in range(2))
-    if _POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(_COPY_THREADS)
-    return _PINNED
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if HOST_TIMES is not None:
+            import time
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if HOST_TIMES is not None:
+            import time
+            HOST_TIMES[self.name] = HOST_TIMES.get(self.name, 0.0) + time.perf_counter() - self.t0
 
 
-def _parallel_copy(dst: np.ndarray, src: np.ndarray):
-    """dst[:] = src for 1-D arrays of equal dtype, split over threads (numpy releases the GIL);
-    a single-threaded memcpy (and first-touch page faults) would cap PCIe staging at ~3 GB/s."""
-    n = dst.shape[0]
-    parts = max(1, min(_COPY_THREADS, (n * dst.itemsize) >> 22))
-    if parts == 1:
-        np.copyto(dst, src)
-        return
-    bounds = [n * i // parts for i in range(parts + 1)]
-    list(_POOL.map(lambda i: np.copyto(dst[bounds[i]:bounds[i + 1]], src[bounds[i]:bounds[i + 1]]), range(parts)))
+def copy_threads() -> int:
+    """Host threads that fill / drain the pinned staging ring: $MUON_B200_COPY_THREADS, else half the cores this
+    process may use divided by the ranks sharing the host (torchrun's LOCAL_WORLD_SIZE), clamped to [4, 48]."""
+    env = os.environ.get("MUON_B200_COPY_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 8
+    local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return int(min(48, max(4, cores // (2 * local))))
+
+
+class Stager:
+    """ctypes handle on a ``mub_stager`` (ring of pinned buffers + host thread pool).  ``pool_only`` builds the
+    thread pool without pinned buffers (host fingerprints only; works without a CUDA device)."""
+
+    def __init__(self, pool_only: bool = False, threads: Optional[int] = None):
+        import ctypes as C
+        self._C = C
+        self.handle = C.c_void_p()
+        self.pool_only = pool_only
+        call("mub_stager_create", _STAGE_BYTES, 0 if pool_only else _STAGE_BUFS, threads or copy_threads(),
+             C.byref(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                load().mub_stager_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def h2d(self, src: np.ndarray, dst: torch.Tensor, narrow: bool = False, want_hash: bool = False, stream=None):
+        """src: contiguous 1-D host array -> dst (device tensor of the same length; int32 when ``narrow``)."""
+        C = self._C
+        h, ov = C.c_uint64(0), C.c_int32(0)
+        assert src.flags.c_contiguous and dst.is_contiguous() and src.shape[0] == dst.numel()
+        eb = src.itemsize if src.itemsize in (4, 8) else 1
+        n = src.shape[0] if eb != 1 else src.nbytes
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
+        with _timed("h2d_s"):
+            call("mub_stager_h2d", self.handle, src.ctypes.data, dst.data_ptr(), n, eb, 1 if narrow else 0,
+                 C.byref(h) if want_hash else None, C.byref(ov), st)
+        if ov.value:
+            raise MuonB200Error("column index does not fit int32 (n_vars >= 2^31 is not supported)")
+        return h.value if want_hash else None
+
+    def d2h(self, src: torch.Tensor, dst: np.ndarray, want_hash: bool = False, stream=None):
+        C = self._C
+        h = C.c_uint64(0)
+        nbytes = src.numel() * src.element_size()
+        assert dst.flags.c_contiguous and dst.nbytes == nbytes and src.is_contiguous()
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
+        with _timed("d2h_s"):
+            call("mub_stager_d2h", self.handle, src.data_ptr(), dst.ctypes.data, nbytes, C.byref(h) if want_hash else None, st)
+        return h.value if want_hash else None
+
+    def fingerprint(self, a: np.ndarray) -> int:
+        """Position-dependent 64-bit fingerprint of a host array of 4-byte elements (or int64, read as int32)."""
+        C = self._C
+        a = np.ascontiguousarray(a).reshape(-1)
+        if a.itemsize not in (4, 8):
+            raise ValueError("fingerprint: 4-byte elements or int64 only")
+        if a.itemsize == 8 and a.dtype != np.int64:
+            a = a.view(np.uint32)
+        h = C.c_uint64(0)
+        with _timed("fingerprint_s"):
+            call("mub_host_fingerprint", self.handle, a.ctypes.data, a.shape[0], a.itemsize, C.byref(h))
+        return h.value
+
+
+_STAGER = None
+_POOL_ONLY = None
+
+
+def stager() -> Stager:
+    global _STAGER
+    if _STAGER is None:
+        _STAGER = Stager()
+    return _STAGER
+
+
+def host_pool() -> Stager:
+    """Thread pool for host fingerprints (the full stager when one exists)."""
+    global _POOL_ONLY
+    if _STAGER is not None:
+        return _STAGER
+    if _POOL_ONLY is None:
+        _POOL_ONLY = Stager(pool_only=True)
+    return _POOL_ONLY
+
+
+def device_fingerprint(t: torch.Tensor) -> int:
+    """The stager's fingerprint of a contiguous device tensor of 4-byte elements."""
+    assert t.is_contiguous() and t.element_size() == 4
+    out = torch.zeros(1, dtype=torch.int64, device=t.device)
+    call("mub_device_fingerprint", ptr(t), t.numel(), ptr(out), stream_ptr())
+    return int(out[0]) & 0xFFFFFFFFFFFFFFFF
+
+
+_SMALL = 8 << 20
 
 
 def to_device(arr, device, dtype=None) -> torch.Tensor:
     """Host array -> device tensor of numpy dtype ``dtype`` (default: unchanged).
 
-    Pinned inputs go in one async copy.  Pageable inputs are staged through two cached pinned
-    buffers (multi-threaded host memcpy overlapping the PCIe copy of the previous chunk); a dtype
-    change (e.g. scipy's int64 indices -> int32) happens on the device per chunk, never on the host."""
+    Small arrays go through torch; large pageable arrays through the native stager (pinned ring filled by a
+    thread pool while the previous chunk is on the bus; scipy's int64 indices are narrowed to int32 on the host
+    inside that copy).  Any other dtype change happens on the device after the upload."""
     if isinstance(arr, torch.Tensor):
         if arr.device.type == "cuda":
             tgt = arr.dtype if dtype is None else getattr(torch, np.dtype(dtype).name)
             return arr if arr.dtype == tgt else arr.to(tgt)
         arr = arr.numpy()
     a = np.ascontiguousarray(arr)
-    tgt = getattr(torch, np.dtype(a.dtype if dtype is None else dtype).name)
-    nbytes = a.nbytes
-    if nbytes <= (8 << 20):
+    tgt_np = np.dtype(a.dtype if dtype is None else dtype)
+    tgt = getattr(torch, tgt_np.name)
+    if a.nbytes <= _SMALL:
         if not a.flags.writeable:
             a = a.copy()
         out = torch.from_numpy(a).to(device, non_blocking=False)
         return out if out.dtype == tgt else out.to(tgt)
-    src_t = getattr(torch, a.dtype.name)
     flat = a.reshape(-1)
-    out = torch.empty(a.shape, dtype=tgt, device=device)
-    flat_dst = out.reshape(-1)
-    stage = _staging()
-    step = _STAGE_BYTES // a.itemsize
-    dstage = [torch.empty(step, dtype=src_t, device=device) for _ in range(2)] if tgt != src_t else None
-    events = [None, None]
-    for i, off in enumerate(range(0, flat.shape[0], step)):
-        n = min(step, flat.shape[0] - off)
-        s = stage[i & 1][: n * a.itemsize].view(src_t)
-        if events[i & 1] is not None:
-            events[i & 1].synchronize()
-        _parallel_copy(s.numpy(), flat[off:off + n])
-        if dstage is None:
-            flat_dst[off:off + n].copy_(s, non_blocking=True)
-        else:
-            dstage[i & 1][:n].copy_(s, non_blocking=True)
-            flat_dst[off:off + n].copy_(dstage[i & 1][:n])
-        ev = torch.cuda.Event()
-        ev.record()
-        events[i & 1] = ev
-    torch.cuda.current_stream().synchronize()
+    if a.dtype == np.int64 and tgt_np == np.int32:
+        out = torch.empty(a.shape, dtype=torch.int32, device=device)
+        stager().h2d(flat, out.reshape(-1), narrow=True)
+        return out
+    raw = torch.empty(a.shape, dtype=getattr(torch, a.dtype.name), device=device)
+    stager().h2d(flat, raw.reshape(-1))
+    if raw.dtype == tgt:
+        return raw
+    out = raw.to(tgt)
+    del raw
     return out
 
 
 def to_host(t: torch.Tensor, out: Optional[np.ndarray] = None) -> np.ndarray:
-    """Device tensor -> numpy array, staged through the pinned buffers for large transfers."""
+    """Device tensor -> numpy array (native stager for large transfers)."""
     np_dt = np.dtype(str(t.dtype).split(".")[1])
     if out is None:
         out = np.empty(tuple(t.shape), dtype=np_dt)
     nbytes = t.numel() * t.element_size()
-    src = t.reshape(-1)
-    dst = out.reshape(-1)
-    if nbytes <= (8 << 20):
-        torch.from_numpy(dst).copy_(src)
+    if nbytes <= _SMALL:
+        torch.from_numpy(out.reshape(-1)).copy_(t.reshape(-1))
         return out
-    stage = _staging()
-    step = _STAGE_BYTES // t.element_size()
-    events, pending = [None, None], [None, None]
-    offs = list(range(0, src.numel(), step))
-    for i, off in enumerate(offs + [None]):
-        if off is not None:
-            n = min(step, src.numel() - off)
-            stage[i & 1][: n * t.element_size()].view(t.dtype).copy_(src[off:off + n], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            events[i & 1], pending[i & 1] = ev, (off, n)
-        j = (i - 1) & 1
-        if i >= 1 and pending[j] is not None:
-            events[j].synchronize()
-            o, n = pending[j]
-            _parallel_copy(dst[o:o + n], stage[j][: n * t.element_size()].view(t.dtype).numpy())
-            pending[j] = None
+    stager().d2h(t.contiguous().reshape(-1), out.reshape(-1))
     return out
 
 
@@ -363,15 +431,53 @@ class TransposedPanels:
             torch.cuda.current_stream().wait_event(self.ready)
             self.ready = None
 
-    def spmm(self, Y: torch.Tensor, dynamic=True) -> torch.Tensor:
+    def spmm(self, Y: torch.Tensor, dynamic=True, half: bool = False) -> torch.Tensor:
+        """A^T Y accumulated panel by panel.  ``half``: round Y to IEEE half first (see ``spmm_h16``)."""
         self.wait()
         out = None
+        Yh = to_half_scaled(Y) if half else None
         for r0, r1, T in self.panels:
-            if out is None:
+            if half:
+                if out is None:
+                    out = spmm_h16(T, Yh[r0:r1], dynamic=dynamic)
+                else:
+                    spmm_h16(T, Yh[r0:r1], out=out, accumulate=True, dynamic=dynamic)
+            elif out is None:
                 out = spmm(T, Y[r0:r1], dynamic=dynamic)
             else:
                 spmm(T, Y[r0:r1], out=out, accumulate=True, dynamic=dynamic)
         return out
+
+
+HALF_SCALE = 32768.0     # 2^15: orthonormal columns (|x| <= 1) stay finite and leave the subnormal range of IEEE half
+
+
+def to_half_scaled(B: torch.Tensor, scale: float = HALF_SCALE) -> torch.Tensor:
+    """fp32 dense operand -> IEEE half of (B * scale), same shape (one fused kernel, 6 B per element)."""
+    assert B.dtype == torch.float32 and B.is_contiguous() and B.numel() % 4 == 0
+    out = torch.empty(B.shape, dtype=torch.float16, device=B.device)
+    call("mub_f32_to_f16_scaled", ptr(B), B.numel(), float(scale), ptr(out), stream_ptr())
+    return out
+
+
+def spmm_h16(A, Bh: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False, dynamic=True,
+             scale: float = HALF_SCALE) -> torch.Tensor:
+    """C[n x P] (+)= A @ (Bh / scale) with the dense operand stored as IEEE half (``to_half_scaled``): half the
+    bytes per non-zero through the L2 -> L1 gather path that bounds the fp32 kernel; fp32 products and sums."""
+    n, d = A.shape
+    P = Bh.shape[1]
+    assert Bh.shape[0] == d and Bh.dtype == torch.float16 and Bh.is_contiguous(), (Bh.shape, d, Bh.dtype)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((n, P), dtype=torch.float32, device=Bh.device)
+    counter = torch.zeros(1, dtype=torch.int64, device=Bh.device) if dynamic else None
+    if isinstance(A, DevicePairs):
+        call("mub_spmm_csrp_h16", ptr(A.indptr), ptr(A.pairs), n, d, ptr(Bh), P, ptr(out), 1 if accumulate else 0,
+             1.0 / scale, ptr(counter), stream_ptr())
+    else:
+        call("mub_spmm_csr_h16", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(Bh), P, ptr(out),
+             1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
+    return out
 
 
 def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False,
@@ -423,86 +529,169 @@ def gram(Y: torch.Tensor, l: Optional[int] = None, weights: Optional[torch.Tenso
 
 
 # ------------------------------------------------------------------------------------------
-# Host matrices produced by tfidf() keep a handle to their device twin so that a following
-# lsi() on the same AnnData does not pay the PCIe upload again.  Before the handle is used every
-# value is compared with the host copy through a 64-bit checksum of the raw bits (one threaded pass
-# over the host array, ~0.2 s for 24 GB, against >2 s for the upload), and the index arrays through
-# a sampled fingerprint -- so editing X on the host between the two calls is safe.
+# Host path of tfidf(): pageable scipy CSR in, pageable scipy CSR out (the reference's contract,
+# muon/_atac/preproc.py:86-129), with the device work hidden under the transfers:
+#   upload  row block b+1 is staged/uploaded on a copy stream while the reduce kernel runs on block b
+#   download the apply kernel of block b+1 runs while block b's values drain to the host
+# Fingerprints of what crossed the bus are a by-product of the staging copies (csrc/staging.cu).
+_BLOCK_NNZ = int(os.environ.get("MUON_B200_BLOCK_NNZ", str(192 << 20)))
+
+
+def _row_blocks(indptr_host: np.ndarray, block_nnz: int):
+    """Cut rows into consecutive blocks of about ``block_nnz`` stored entries -> list of (r0, r1, k0, k1)."""
+    n = indptr_host.shape[0] - 1
+    nnz = int(indptr_host[-1])
+    if n == 0:
+        return []
+    nb = max(1, -(-nnz // max(block_nnz, 1)))
+    targets = (np.arange(1, nb, dtype=np.float64) * (nnz / nb)).astype(np.int64)
+    cuts = np.unique(np.concatenate([[0], np.searchsorted(indptr_host, targets, side="left"), [n]]))
+    return [(int(a), int(b), int(indptr_host[a]), int(indptr_host[b])) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+
+def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=1e4):
+    """float32 scipy CSR on the host -> (DeviceCSR holding the TF-IDF values, host value array, fingerprints),
+    or None if the input is not canonical (the caller canonicalises and retries).
+
+    Same kernels as ``tfidf_csr``; the host<->device copies are pipelined with them as described above."""
+    require_cuda()
+    assert X.data.dtype == np.float32
+    n, d = X.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    flags = (TFIDF_LOG_TF if log_tf else 0) | (TFIDF_LOG_IDF if log_idf else 0) | (TFIDF_LOG_TFIDF if log_tfidf else 0)
+    if scale_factor is None or scale_factor == 0 or scale_factor == 1:
+        flags |= TFIDF_NO_SCALE
+        scale_factor = 1.0
+    indptr_h = np.ascontiguousarray(X.indptr)
+    indices_h = np.ascontiguousarray(X.indices)
+    data_h = np.ascontiguousarray(X.data)
+    nnz = int(indptr_h[-1]) if indptr_h.shape[0] else 0
+    blocks = _row_blocks(indptr_h, _BLOCK_NNZ)
+    st = stager()
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    indptr = to_device(indptr_h, dev, np.int64)
+    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    data = torch.empty(nnz, dtype=torch.float32, device=dev)
+    row_sum = torch.empty(n, dtype=torch.float32, device=dev)
+    col_sum = torch.zeros(d, dtype=torch.float32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    side.wait_stream(main)                      # allocations above are ordered on the main stream
+    narrow = indices_h.dtype == np.int64
+    assert narrow or indices_h.dtype == np.int32, indices_h.dtype
+    fp_idx, fp_out = [], []
+    for (r0, r1, k0, k1) in blocks:
+        fp_idx.append(st.h2d(indices_h[k0:k1], indices[k0:k1], narrow=narrow, want_hash=True, stream=side))
+        st.h2d(data_h[k0:k1], data[k0:k1], stream=side)
+        main.wait_event(side.record_event())
+        call("mub_tfidf_reduce_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,
+             ptr(col_sum), ptr(status), flags, main.cuda_stream)
+    for t in (indices, data):
+        t.record_stream(side)
+    if int(status[0]) != 0:                     # duplicates / explicit zeros / unsorted rows (also syncs the upload)
+        return None
+    _dist.all_reduce_sum_(col_sum)
+    idf = torch.empty(d, dtype=torch.float32, device=dev)
+    n_total = n
+    if _dist.is_distributed():
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        n_total = int(_dist.all_reduce_sum_(t)[0])
+    call("mub_tfidf_idf_f32", ptr(col_sum), d, float(n_total), flags, ptr(idf), main.cuda_stream)
+    with _timed("alloc_out_s"):
+        out_h = np.empty(nnz, dtype=np.float32)
+
+    def apply(b):
+        r0, r1, k0, k1 = blocks[b]
+        call("mub_tfidf_apply_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), ptr(data), r1 - r0, d,
+             ptr(row_sum) + 4 * r0, ptr(idf), float(scale_factor), flags, main.cuda_stream)
+        return main.record_event()
+
+    ev = apply(0) if blocks else None
+    for b, (r0, r1, k0, k1) in enumerate(blocks):
+        ev_next = apply(b + 1) if b + 1 < len(blocks) else None
+        side.wait_event(ev)
+        fp_out.append(st.d2h(data[k0:k1], out_h[k0:k1], want_hash=True, stream=side))
+        ev = ev_next
+    main.wait_stream(side)
+    res = DeviceCSR(indptr, indices, data, (n, d), n_total=n_total)
+    res._aux = {"row_sum": row_sum, "col_sum": col_sum, "idf": idf}
+    fps = {"blocks": [(k0, k1) for (_, _, k0, k1) in blocks], "indices": fp_idx, "data": fp_out,
+           "indptr": host_pool().fingerprint(indptr_h.astype(np.int64, copy=False).view(np.uint32)) if n else 0}
+    return res, out_h, fps
+
+
+# ------------------------------------------------------------------------------------------
+# Device twins.  A host matrix produced by tfidf() keeps a handle on the DeviceCSR it was downloaded from so
+# that a following lsi()/mofa() on the same AnnData skips the 48 GB re-upload.  The twin is used only after
+# EVERY element of the host matrix's data, indices and indptr has been re-fingerprinted (position-dependent,
+# csrc/staging.cu) and found equal to what crossed the bus -- one threaded read pass over the host arrays, no
+# device work -- so any host-side edit between the two calls (values, order, a single index) falls back to a
+# fresh upload.  $MUON_B200_RESIDENT=0 disables twins; release_resident() / release_all_resident() free the HBM
+# explicitly (a twin otherwise lives as long as the host matrix it is attached to).
 _RESIDENT_ATTR = "_mub_resident"
+_RESIDENT_REGISTRY = None
 
 
-def _bits_checksum_host(a: np.ndarray) -> int:
-    """Sum of the array's bytes read as int64 words, modulo 2^64 (tail bytes zero-padded)."""
-    if a.size == 0:
-        return 0
-    raw = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
-    n8 = raw.shape[0] // 8
-    words = raw[: n8 * 8].view(np.int64)
-    pool = _checksum_pool()
-    parts = max(1, min(pool._max_workers, (n8 * 8) >> 22))
-    bounds = [n8 * i // parts for i in range(parts + 1)]
-    with np.errstate(over="ignore"):
-        sums = list(pool.map(lambda i: int(np.add.reduce(words[bounds[i]:bounds[i + 1]], dtype=np.int64)), range(parts)))
-    tail = bytes(raw[n8 * 8:]) + b"\0" * (8 - (raw.shape[0] - n8 * 8)) if raw.shape[0] > n8 * 8 else b""
-    total = sum(sums) + (int.from_bytes(tail, "little", signed=True) if tail else 0)
-    return total & 0xFFFFFFFFFFFFFFFF
+def resident_enabled() -> bool:
+    return os.environ.get("MUON_B200_RESIDENT", "1") != "0"
 
 
-def _bits_checksum_device(t: torch.Tensor) -> int:
-    """Same checksum of a contiguous device (or CPU) tensor; chunked so that no large temporary is made."""
-    if t.numel() == 0:
-        return 0
-    raw = t.contiguous().reshape(-1).view(torch.uint8)
-    n8 = raw.numel() // 8
-    words = raw[: n8 * 8].view(torch.int64)
-    total = 0
-    step = 1 << 28
-    for off in range(0, n8, step):
-        total += int(words[off:off + step].sum())          # int64 accumulation wraps like the host sum
-    if raw.numel() > n8 * 8:
-        tail = bytes(raw[n8 * 8:].cpu().numpy()) + b"\0" * (8 - (raw.numel() - n8 * 8))
-        total += int.from_bytes(tail, "little", signed=True)
-    return total & 0xFFFFFFFFFFFFFFFF
-
-
-_SUM_POOL = None
-
-
-def _checksum_pool():
-    global _SUM_POOL
-    if _SUM_POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _SUM_POOL = ThreadPoolExecutor(max(1, min(32, os.cpu_count() or 1)))   # read-only pass: more threads than the memcpy
-    return _SUM_POOL
-
-
-def remember_resident(host_matrix, dev: "DeviceCSR"):
+def remember_resident(host_matrix, dev: "DeviceCSR", fingerprints: dict):
+    global _RESIDENT_REGISTRY
+    if not resident_enabled():
+        return
     try:
-        setattr(host_matrix, _RESIDENT_ATTR, dev)
+        setattr(host_matrix, _RESIDENT_ATTR, (dev, fingerprints))
+        import weakref
+        if _RESIDENT_REGISTRY is None:
+            _RESIDENT_REGISTRY = weakref.WeakSet()
+        _RESIDENT_REGISTRY.add(host_matrix)
     except Exception:
         pass
 
 
+def release_resident(obj) -> bool:
+    """Drop the device twin attached to a host matrix (or to ``adata.X`` / every layer of an AnnData-like
+    object).  Returns True if something was released."""
+    done = False
+    for m in [obj, getattr(obj, "X", None)] + list(getattr(obj, "layers", {}).values() if hasattr(obj, "layers") else []):
+        if m is not None and getattr(m, _RESIDENT_ATTR, None) is not None:
+            try:
+                delattr(m, _RESIDENT_ATTR)
+                done = True
+            except Exception:
+                pass
+    return done
+
+
+def release_all_resident() -> int:
+    """Drop every live device twin (e.g. before a memory-hungry mofa()/neighbors() call)."""
+    n = 0
+    if _RESIDENT_REGISTRY is not None:
+        for m in list(_RESIDENT_REGISTRY):
+            n += bool(release_resident(m))
+    return n
+
+
 def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
-    dev = getattr(host_matrix, _RESIDENT_ATTR, None)
-    if dev is None or not isinstance(dev, DeviceCSR):
+    rec = getattr(host_matrix, _RESIDENT_ATTR, None)
+    if rec is None or not resident_enabled():
         return None
     try:
-        if tuple(dev.shape) != tuple(host_matrix.shape) or dev.nnz != host_matrix.nnz:
+        dev, fps = rec
+        if not isinstance(dev, DeviceCSR) or tuple(dev.shape) != tuple(host_matrix.shape) or dev.nnz != host_matrix.nnz:
             return None
         if host_matrix.data.dtype != np.float32 or dev.data.dtype != torch.float32:
             return None
-        nnz = dev.nnz
-        if nnz:
-            pos = np.unique(np.linspace(0, nnz - 1, num=min(nnz, 4096), dtype=np.int64))
-            idx = torch.from_numpy(pos).to(dev.data.device)
-            if not np.array_equal(dev.indices[idx].cpu().numpy(), np.asarray(host_matrix.indices[pos], dtype=np.int32)):
-                return None
-            rows = np.unique(np.linspace(0, dev.shape[0], num=min(dev.shape[0] + 1, 4096), dtype=np.int64))
-            if not np.array_equal(dev.indptr[torch.from_numpy(rows).to(dev.data.device)].cpu().numpy(),
-                                  np.asarray(host_matrix.indptr[rows], dtype=np.int64)):
-                return None
-            if _bits_checksum_device(dev.data) != _bits_checksum_host(host_matrix.data):
+        if host_matrix.indices.dtype not in (np.int32, np.int64):
+            return None
+        pool = host_pool()
+        indptr = np.ascontiguousarray(host_matrix.indptr).astype(np.int64, copy=False)
+        if indptr.shape[0] != dev.shape[0] + 1 or pool.fingerprint(indptr.view(np.uint32)) != fps["indptr"]:
+            return None
+        idx, dat = np.ascontiguousarray(host_matrix.indices), np.ascontiguousarray(host_matrix.data)
+        for (k0, k1), hi, hd in zip(fps["blocks"], fps["indices"], fps["data"]):
+            if pool.fingerprint(dat[k0:k1]) != hd or pool.fingerprint(idx[k0:k1]) != hi:
                 return None
         return dev
     except Exception:

@@ -46,6 +46,15 @@ SIGNATURES = {
     "mub_knn_l2_tc_f32": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp, vp],
     "mub_wnn_bandwidth_f32": [vp, vp, vp, vp, vp, i64, i32, i32, i32, f64, vp, vp, vp, i64, vp, i32, i32, vp],
     "mub_wnn_affinity_topk_f32": [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp, vp, vp, vp],
+    "mub_f32_to_f16_scaled": [vp, i64, f32, vp, vp],
+    "mub_spmm_csr_h16": [vp, vp, vp, i64, i64, vp, i32, vp, i32, f32, vp, vp],
+    "mub_spmm_csrp_h16": [vp, vp, i64, i64, vp, i32, vp, i32, f32, vp, vp],
+    "mub_stager_create": [C.c_size_t, i32, i32, C.POINTER(vp)],
+    "mub_stager_destroy": [vp],
+    "mub_stager_h2d": [vp, vp, vp, C.c_size_t, i32, i32, C.POINTER(u64), C.POINTER(i32), vp],
+    "mub_stager_d2h": [vp, vp, vp, C.c_size_t, C.POINTER(u64), vp],
+    "mub_host_fingerprint": [vp, vp, C.c_size_t, i32, C.POINTER(u64)],
+    "mub_device_fingerprint": [vp, i64, vp, vp],
     "mub_synth_count": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp],
     "mub_synth_fill": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp, vp, vp],
 }
@@ -90,7 +99,8 @@ def load():
 
 
 # kernels launched per successful call (for the benchmark's gpu_launches claim)
-KERNELS_PER_CALL = {"mub_csr_transpose_fill": 2, "mub_csr_transpose_fill_pairs": 2, "mub_gram_f32": 2, "mub_version": 0, "mub_device_info": 0}
+KERNELS_PER_CALL = {"mub_csr_transpose_fill": 2, "mub_csr_transpose_fill_pairs": 2, "mub_gram_f32": 2, "mub_version": 0, "mub_device_info": 0,
+                    "mub_stager_create": 0, "mub_stager_destroy": 0, "mub_stager_h2d": 0, "mub_stager_d2h": 0, "mub_host_fingerprint": 0}
 LAUNCHES = 0          # running count of kernels launched through this binding
 PROFILE = None        # None, or dict name -> list[(start_event, end_event)] filled by call()
 

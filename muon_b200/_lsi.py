@@ -41,6 +41,7 @@ from ._lib import phase
 @dataclass
 class SvdInfo:
     passes: int = 0              # sparse passes over A or A^T
+    lowp_passes: int = 0         # of which with the dense operand rounded to IEEE half
     iterations: int = 0
     restarts: int = 0
     basis: int = 0
@@ -65,15 +66,19 @@ class CsrOperator:
         self.device = A.data.device
         self.passes = 0
 
-    def av(self, V):
+    lowp = True      # av / aty accept lowp=True: dense operand rounded to IEEE half (csrc/spmm.cu, spmm_row_h)
+
+    def av(self, V, lowp: bool = False):
         self.passes += 1
         with phase("lsi.spmm_av"):
+            if lowp:
+                return self._dev.spmm_h16(self.A, self._dev.to_half_scaled(V), dynamic=False)
             return self._dev.spmm(self.A, V, dynamic=False)
 
-    def aty(self, Y):
+    def aty(self, Y, lowp: bool = False):
         self.passes += 1
         with phase("lsi.spmm_aty"):
-            W = self.At.spmm(Y, dynamic=True)
+            W = self.At.spmm(Y, dynamic=True, half=lowp)
             return _dist.all_reduce_sum_(W)
 
     def gram(self, Y, l):
@@ -161,7 +166,8 @@ def _orth_against(W: torch.Tensor, Q: torch.Tensor, passes: int = 2):
 
 
 def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optional[int] = None,
-                  max_restarts: int = 4, seed: int = 0, verbose: bool = False, polish: Optional[bool] = None):
+                  max_restarts: int = 4, seed: int = 0, verbose: bool = False, polish: Optional[bool] = None,
+                  lowp_tol: Optional[float] = None):
     """Top-k singular triplets of the (cell-sharded) matrix behind ``op``.
 
     Returns (U [n_local x k] fp32, s [k] fp64, V [d x k] fp32, SvdInfo).  ``pad_to`` is the padded
@@ -171,9 +177,20 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
     ``False`` returns the Ritz triplets of the Krylov spaces themselves -- U_k from the stored left blocks -- and
     saves that pass; on the CPU driver tests both are equally accurate (sigma 1e-7, vectors < 1e-6), the GPU parity
     suite has only been run with the polish so far, hence the default.
+
+    ``lowp_tol`` (default: $MUON_B200_LSI_LOWP_TOL, "0" = off): if > ``tol`` and the operator supports it
+    (``op.lowp``), the iteration first runs with the dense operand of every product rounded to IEEE half -- half the
+    bytes through the gather path that bounds the SpMM kernel -- until the wanted triplets reach ``lowp_tol``
+    (rounding to half caps the attainable residual near 2e-4, so 1e-3 is the useful setting), then restarts in
+    fp32 from the Ritz vectors: one fp32 block step takes residuals from ~3e-4 to below 1e-5.  The result is the
+    fp32 iteration's own (same stopping rule, same Rayleigh-Ritz tail); only the path to the final subspace is
+    cheaper.  ``SvdInfo.lowp_passes`` counts the half-precision passes.
     """
     if polish is None:
         polish = os.environ.get("MUON_B200_LSI_POLISH", "1") != "0"
+    if lowp_tol is None:
+        lowp_tol = float(os.environ.get("MUON_B200_LSI_LOWP_TOL", "0") or 0.0)
+    lowp = bool(getattr(op, "lowp", False)) and lowp_tol > tol
     d, dev, P = op.d, op.device, pad_to
     k = int(k)
     b = min(P, d, getattr(op, "n_total", d))
@@ -188,26 +205,36 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
         V0 = torch.randn((d, b), generator=g, dtype=torch.float32, device=dev)
         V0, _ = _qr_dspace(op, V0, P)
 
+    def _av(V):
+        return op.av(V, lowp=True) if lowp else op.av(V)
+
+    def _aty(Y):
+        return op.aty(Y, lowp=True) if lowp else op.aty(Y)
+
     Vk = None
-    for restart in range(max_restarts + 1):
+    restart = 0
+    while True:
         Vall = torch.empty((d, m_cap), dtype=torch.float32, device=dev)
         Bmat = torch.zeros((m_cap, m_cap), dtype=f64, device=dev)
         Vall[:, :b] = V0
         m = b                                  # columns of Vall in use
-        Y = op.av(_pad(Vall[:, :b], P))
+        Y = _av(_pad(Vall[:, :b], P))
         info.passes += 1
+        info.lowp_passes += int(lowp)
         U, R = _cholqr2(op, Y, b)              # U: n x P (cols >= b are zero)
         Bmat[:b, :b] = R
         blocks = [(0, b)]                      # column ranges of the blocks
-        Ublocks = None if polish else [U[:, :b].clone()]   # left Lanczos blocks (only needed without the polish)
+        Ublocks = None if (polish or lowp) else [U[:, :b].clone()]   # left Lanczos blocks (only needed without the polish)
         prev_res, stagn = None, 0
         done = False
+        target = lowp_tol if lowp else tol
         while True:
             j0, j1 = blocks[-1]
             bj = j1 - j0
             # ---- right side: W = A^T U_j - V_j R_j^T, full reorth, QR --------------------
-            W = op.aty(U)[:, :bj].clone()
+            W = _aty(U)[:, :bj].clone()
             info.passes += 1
+            info.lowp_passes += int(lowp)
             with phase("lsi.reorth"):
                 W -= Vall[:, j0:j1] @ Bmat[j0:j1, j0:j1].T.to(torch.float32)
                 W, _ = _orth_against(W, Vall[:, :m])
@@ -250,8 +277,8 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
             else:
                 stagn = 0
             prev_res = rmax
-            if rmax <= tol or stagn >= 2 or bn <= 0:
-                done = (rmax <= tol) or stagn >= 2 or m >= d
+            if rmax <= target or stagn >= 2 or bn <= 0:
+                done = (rmax <= target) or stagn >= 2 or m >= d
                 info.residuals = res.tolist()
                 with phase("lsi.ritz_vectors"):
                     Vk = Vall[:, :m] @ Zt[:kk, :].T.to(torch.float32)      # d x k right Ritz vectors
@@ -264,8 +291,9 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
             # ---- left side: Y = A V_{j+1} - U_j S_j^T, CholeskyQR2 --------------------------
             Sj_use = Sj[:bn, :]                                    # if the block shrank keep bn rows
             Vall[:, m:m + bn] = Qn[:, :bn]
-            Y = op.av(_pad(Vall[:, m:m + bn], P))
+            Y = _av(_pad(Vall[:, m:m + bn], P))
             info.passes += 1
+            info.lowp_passes += int(lowp)
             with phase("lsi.left_update"):
                 M = torch.zeros((P, P), dtype=torch.float32, device=dev)
                 M[:bj, :bn] = Sj_use.T.to(torch.float32)
@@ -277,11 +305,17 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
             if Ublocks is not None:
                 Ublocks.append(U[:, :bn].clone())
             m += bn
+        if lowp:
+            # half-precision phase over: continue in fp32 from its Ritz vectors (not counted as a restart)
+            lowp = False
+            V0, _ = torch.linalg.qr(V0_next)
+            continue
         info.basis = m
         info.converged = (rmax <= tol) or m >= d
         info.stalled = done and not info.converged
         if done or restart == max_restarts:
             break
+        restart += 1
         info.restarts += 1
         V0, _ = torch.linalg.qr(V0_next)
 

@@ -88,9 +88,31 @@ def make_tables(n_cols: int, density: float, n_topics: int = 64, seed: int = 0) 
 _GEOM_THR = np.array([2576980378, 3607772529, 4020089389, 4185016133], dtype=np.uint64)
 
 
+def _host_chunk(tb, seedmix, j, half_beta, rt, rs, n_cols, row_lo, row_hi, c0, c1):
+    """Rows [c0, c1) of the chunked generator (numpy releases the GIL inside these array operations)."""
+    base = (half_beta[None, :] + tb.topic[rt[c0:c1]]).astype(np.float32)
+    np.multiply(base, rs[c0:c1, None], out=base)
+    np.minimum(base, np.float32(0.9), out=base)
+    thr = (base * np.float32(4294967296.0)).astype(np.uint32)
+    del base
+    with np.errstate(over="ignore"):
+        rowkey = seedmix + (np.arange(row_lo + c0, row_lo + c1, dtype=np.uint64) * np.uint64(n_cols))
+        h = mix64(rowkey[:, None] + j[None, :])
+    keep = (h >> np.uint64(32)).astype(np.uint32) < thr
+    del thr
+    r, c = np.nonzero(keep)
+    lo = h[r, c] & np.uint64(0xFFFFFFFF)
+    del h, keep
+    val = np.float32(1.0) + (lo[:, None] >= _GEOM_THR[None, :]).sum(1).astype(np.float32)
+    return np.bincount(r, minlength=c1 - c0), c.astype(np.int32), val.astype(np.float32)
+
+
 def generate_host(n_rows: int, n_cols: int, density: float, n_topics: int = 64, seed: int = 0,
-                  row0: int = 0, tables: SynthTables = None, chunk: int = 256):
-    """numpy twin of the device generator -> scipy.sparse.csr_matrix (float32, sorted int32 indices)."""
+                  row0: int = 0, tables: SynthTables = None, chunk: int = 64, threads: int = None):
+    """numpy twin of the device generator -> scipy.sparse.csr_matrix (float32, sorted int32 indices).
+    Row chunks are generated on a thread pool (``threads``: default min(32, cores))."""
+    import os
+
     import scipy.sparse as sp
     tb = tables or make_tables(n_cols, density, n_topics, seed)
     rt, rs = tb.rows(row0, n_rows)
@@ -98,26 +120,25 @@ def generate_host(n_rows: int, n_cols: int, density: float, n_topics: int = 64, 
     j = np.arange(n_cols, dtype=np.uint64)
     half_beta = np.float32(0.5) * tb.beta
     indptr = np.zeros(n_rows + 1, dtype=np.int64)
-    idx_parts, val_parts = [], []
-    for c0 in range(0, n_rows, chunk):
-        c1 = min(n_rows, c0 + chunk)
-        base = (half_beta[None, :] + tb.topic[rt[c0:c1]]).astype(np.float32)
-        p = np.minimum(base * rs[c0:c1, None], np.float32(0.9)).astype(np.float32)
-        thr = (p * np.float32(4294967296.0)).astype(np.uint32)
-        with np.errstate(over="ignore"):
-            rowkey = seedmix + (np.arange(row0 + c0, row0 + c1, dtype=np.uint64) * np.uint64(n_cols))
-            h = mix64(rowkey[:, None] + j[None, :])
-        keep = (h >> np.uint64(32)).astype(np.uint32) < thr
-        lo = h & np.uint64(0xFFFFFFFF)
-        r, c = np.nonzero(keep)
-        lo = lo[r, c]
-        val = np.float32(1.0) + (lo[:, None] >= _GEOM_THR[None, :]).sum(1).astype(np.float32)
-        indptr[c0 + 1:c1 + 1] = np.bincount(r, minlength=c1 - c0)
-        idx_parts.append(c.astype(np.int32))
-        val_parts.append(val.astype(np.float32))
+    starts = list(range(0, n_rows, chunk))
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except Exception:
+            threads = os.cpu_count() or 1
+        threads = min(32, threads)
+    work = lambda c0: _host_chunk(tb, seedmix, j, half_beta, rt, rs, n_cols, row0, None, c0, min(n_rows, c0 + chunk))  # noqa: E731
+    if threads > 1 and len(starts) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as pool:
+            parts = list(pool.map(work, starts))
+    else:
+        parts = [work(c0) for c0 in starts]
+    for c0, (cnt, _, _) in zip(starts, parts):
+        indptr[c0 + 1:c0 + 1 + cnt.shape[0]] = cnt
     indptr = np.cumsum(indptr)
-    indices = np.concatenate(idx_parts) if idx_parts else np.zeros(0, np.int32)
-    data = np.concatenate(val_parts) if val_parts else np.zeros(0, np.float32)
+    indices = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int32)
+    data = np.concatenate([p[2] for p in parts]) if parts else np.zeros(0, np.float32)
     if indptr[-1] < 2**31 - 1:
         indptr = indptr.astype(np.int32)
     X = sp.csr_matrix((data, indices, indptr), shape=(n_rows, n_cols))

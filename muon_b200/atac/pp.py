@@ -75,19 +75,34 @@ def tfidf(
         import scipy.sparse as sp
         X = counts if sp.isspmatrix_csr(counts) else sp.csr_matrix(counts)
         cdt = X.dtype if X.dtype in (np.float32, np.float64) else np.float64  # ints -> f64, App. A.2
-        out = None
+        # The device never touches the sparsity pattern, so the result reuses the host index arrays -- but only
+        # when it REPLACES the matrix it was computed from (adata.X = res).  If source and result both stay
+        # alive (inplace=False, layers) they get their own arrays, like the reference's np.dot(dia, counts).
+        replaces_source = inplace and from_layer is None and to_layer is None and X is counts
+        res = None
         for attempt in range(2):
-            dev = _device.DeviceCSR.from_scipy(X, dtype=cdt)
-            # the kernel itself verifies canonical form while it reduces (no host scan of 6e9 nnz)
-            out = _device.tfidf_csr(dev, log_tf, log_idf, log_tfidf, scale_factor, inplace_values=True,
-                                    check_canonical=(attempt == 0))
-            if out is not None:
-                break
+            if cdt == np.float32 and X.indices.dtype in (np.int32, np.int64) and X.nnz > 0:
+                got = _device.tfidf_from_host(X, log_tf, log_idf, log_tfidf, scale_factor)   # pipelined with the copies
+                if got is not None:
+                    out, values, fps = got
+                    res = sp.csr_matrix(X.shape, dtype=np.float32)
+                    res.data = values
+                    res.indices = X.indices if replaces_source else X.indices.copy()
+                    res.indptr = X.indptr if replaces_source else X.indptr.copy()
+                    res.has_sorted_indices = True
+                    _device.remember_resident(res, out, fps)  # lets lsi() skip the re-upload
+                    break
+            else:
+                dev = _device.DeviceCSR.from_scipy(X, dtype=cdt)
+                # the kernel itself verifies canonical form while it reduces (no host scan of 6e9 nnz)
+                out = _device.tfidf_csr(dev, log_tf, log_idf, log_tfidf, scale_factor, inplace_values=True,
+                                        check_canonical=(attempt == 0))
+                if out is not None:
+                    res = out.get(indptr_host=X.indptr if replaces_source else X.indptr.copy(),
+                                  indices_host=X.indices if replaces_source else X.indices.copy())
+                    break
             X = _canonical_csr(X)
-        # the sparsity pattern is untouched on the device: reuse the host index arrays
-        res = out.get(indptr_host=X.indptr, indices_host=X.indices)
-        if cdt == np.float32:
-            _device.remember_resident(res, out)  # lets lsi() skip the re-upload
+            replaces_source = False
 
     if not inplace:
         return res

@@ -88,6 +88,11 @@ __device__ __forceinline__ float4 ld_gather4(const float* p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint4 ld_gather_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 // streaming store
 __device__ __forceinline__ void st_stream(float* p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" ::"l"(p), "f"(v));

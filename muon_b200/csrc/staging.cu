@@ -1,0 +1,388 @@
+// Host <-> device staging engine for the ingest side of the hot path.
+//
+// The reference keeps AnnData.X as a pageable scipy CSR in host memory (muon/_atac/preproc.py:86-129
+// reads adata.X / adata.layers[...] and rebinds a freshly allocated matrix).  A drop-in GPU path
+// therefore starts and ends in pageable memory: 72 GB in / 24 GB out at BASELINE configs[1].
+// cudaMemcpy from pageable memory runs at a few GB/s, so transfers are staged through a small ring
+// of pinned buffers that a pool of host threads fills (H2D) or drains (D2H) while the DMA engine
+// works on the previous chunk.  Two things are fused into that copy so that no byte of host memory
+// is touched twice:
+//   * narrowing of scipy's int64 index arrays (nnz >= 2^31) to the int32 the kernels use,
+//   * a position-dependent 64-bit fingerprint of the element stream, which lets a later call
+//     prove that a host array still equals its device twin without a device pass.
+//
+// Pure host code (std::thread + cudaMemcpyAsync); compiled by nvcc with the rest of the library.
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mub {
+
+// ---- fingerprint: H = sum_i (e_i + C1) * (i * C2 + C3)  mod 2^64 over 32-bit elements e_i.  Every
+// term carries its position, so partial sums over disjoint ranges just add up (thread- and
+// chunk-order independent) while any permutation or single-element edit changes the value.
+constexpr uint64_t kH1 = 0x9E3779B97F4A7C15ull, kH2 = 0xD6E8FEB86659FD93ull, kH3 = 0xA0761D6478BD642Full;
+
+__host__ __device__ inline uint64_t hash_term(uint32_t e, uint64_t i) {
+    return ((uint64_t)e + kH1) * (i * kH2 + kH3);
+}
+
+// copy `n` elements starting at logical position `pos0`; returns their fingerprint contribution
+static uint64_t copy_hash_u32(uint32_t* dst, const uint32_t* src, size_t n, uint64_t pos0, bool want_hash) {
+    if (!want_hash) {
+        memcpy(dst, src, n * 4);
+        return 0;
+    }
+    uint64_t h = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t e = src[i];
+        dst[i] = e;
+        h += hash_term(e, pos0 + i);
+    }
+    return h;
+}
+
+static uint64_t narrow_hash_i64(int32_t* dst, const int64_t* src, size_t n, uint64_t pos0, bool want_hash,
+                                int* overflow) {
+    uint64_t h = 0;
+    int bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const int64_t v = src[i];
+        bad |= (v != (int64_t)(int32_t)v);
+        dst[i] = (int32_t)v;
+        if (want_hash) h += hash_term((uint32_t)(int32_t)v, pos0 + i);
+    }
+    if (bad) *overflow = 1;
+    return h;
+}
+
+static uint64_t hash_only(const void* src, size_t n, int elem_bytes, uint64_t pos0) {
+    uint64_t h = 0;
+    if (elem_bytes == 8) {
+        const int64_t* s = (const int64_t*)src;
+        for (size_t i = 0; i < n; ++i) h += hash_term((uint32_t)(int32_t)s[i], pos0 + i);
+    } else {
+        const uint32_t* s = (const uint32_t*)src;
+        for (size_t i = 0; i < n; ++i) h += hash_term(s[i], pos0 + i);
+    }
+    return h;
+}
+
+// ---- a small persistent worker pool: run(fn, parts) executes fn(part) for part in [0, parts) ------
+class Pool {
+  public:
+    explicit Pool(int n) : n_(n < 1 ? 1 : n) {
+        for (int t = 0; t < n_ - 1; ++t) threads_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    void run(const std::function<void(int)>& fn, int parts) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn;
+            parts_ = parts;
+            next_ = 0;
+            pending_ = parts;
+            ++gen_;
+        }
+        cv_.notify_all();
+        work();  // the calling thread takes parts too
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+        parts_ = next_ = 0;
+    }
+
+  private:
+    // every piece of shared state is read and written under m_ (a run hands out at most a few dozen parts,
+    // each worth >= 100 us of copying, so the lock is never contended for long)
+    void work() {
+        for (;;) {
+            const std::function<void(int)>* fn;
+            int p;
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (fn_ == nullptr || next_ >= parts_) return;
+                p = next_++;
+                fn = fn_;
+            }
+            (*fn)(p);
+            std::lock_guard<std::mutex> g(m_);
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int parts_ = 0, pending_ = 0;
+    int next_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+struct Stager {
+    size_t buf_bytes = 0;
+    int n_bufs = 0;
+    std::vector<void*> bufs;
+    std::vector<cudaEvent_t> events;
+    Pool* pool = nullptr;
+};
+
+#define MUB_CUDA(call, what)                                          \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) {                                      \
+            mub::set_error("%s: %s", what, cudaGetErrorString(e_));   \
+            return -2;                                                \
+        }                                                             \
+    } while (0)
+
+}  // namespace mub
+
+extern "C" {
+
+int mub_stager_create(size_t buf_bytes, int32_t n_bufs, int32_t n_threads, void** out) {
+    MUB_REQUIRE(out != nullptr, "stager_create: null out");
+    // n_bufs == 0: thread pool only (host fingerprints; needs no CUDA context)
+    MUB_REQUIRE(buf_bytes >= 4096 && (buf_bytes % 16) == 0 && (n_bufs == 0 || (n_bufs >= 2 && n_bufs <= 64)) && n_threads >= 1,
+                "stager_create: need buf_bytes >= 4096 (multiple of 16), 0 or 2..64 buffers, >=1 thread");
+    auto* s = new mub::Stager();
+    s->buf_bytes = buf_bytes;
+    s->n_bufs = n_bufs;
+    for (int i = 0; i < n_bufs; ++i) {
+        void* p = nullptr;
+        cudaError_t e = cudaHostAlloc(&p, buf_bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            mub::set_error("stager_create: cudaHostAlloc(%zu): %s", buf_bytes, cudaGetErrorString(e));
+            for (void* q : s->bufs) cudaFreeHost(q);
+            for (auto ev : s->events) cudaEventDestroy(ev);
+            delete s;
+            return -2;
+        }
+        s->bufs.push_back(p);
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        s->events.push_back(ev);
+    }
+    s->pool = new mub::Pool(n_threads);
+    *out = s;
+    return 0;
+}
+
+int mub_stager_destroy(void* handle) {
+    if (!handle) return 0;
+    auto* s = (mub::Stager*)handle;
+    delete s->pool;
+    for (void* p : s->bufs) cudaFreeHost(p);
+    for (auto ev : s->events) cudaEventDestroy(ev);
+    delete s;
+    return 0;
+}
+
+// Pageable host -> device.  src_elem_bytes: 4 or 8 (bytes of one source element);  narrow != 0 (only with
+// 8-byte sources): int64 -> int32 on the host while staging; a value outside int32 sets *overflow_h.
+// hash_h (optional): fingerprint of the uploaded stream as 32-bit elements (4-byte sources, or narrowed
+// 8-byte sources).  All chunks are enqueued on `stream`; returns once the last chunk is enqueued (the
+// staging buffers are guarded by events, so the call may be followed by another one immediately).
+int mub_stager_h2d(void* handle, const void* src_h, void* dst, size_t n_elems, int32_t src_elem_bytes, int32_t narrow,
+                   uint64_t* hash_h, int32_t* overflow_h, mub_stream_t stream) {
+    using namespace mub;
+    MUB_REQUIRE(handle != nullptr && ((mub::Stager*)handle)->n_bufs >= 2, "stager_h2d: stager has no staging buffers");
+    MUB_REQUIRE(src_elem_bytes == 4 || src_elem_bytes == 8 || src_elem_bytes == 1, "stager_h2d: element size must be 1, 4 or 8");
+    MUB_REQUIRE(!narrow || src_elem_bytes == 8, "stager_h2d: narrowing needs 8-byte source elements");
+    MUB_REQUIRE(!hash_h || src_elem_bytes == 4 || narrow, "stager_h2d: fingerprint needs 32-bit elements");
+    if (hash_h) *hash_h = 0;
+    if (n_elems == 0) return 0;
+    MUB_REQUIRE(src_h && dst, "stager_h2d: null pointer");
+    auto* s = (Stager*)handle;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t dst_elem = narrow ? 4 : (size_t)src_elem_bytes;
+    const size_t per_chunk = s->buf_bytes / dst_elem;
+    const int T = s->pool->size();
+    std::vector<uint64_t> partial(T, 0);
+    int overflow = 0;
+    uint64_t hash = 0;
+    size_t off = 0;
+    for (size_t c = 0; off < n_elems; ++c, off += per_chunk) {
+        const int b = (int)(c % s->n_bufs);
+        const size_t cnt = n_elems - off < per_chunk ? n_elems - off : per_chunk;
+        // the buffer may still feed a DMA of this or of an earlier transfer (possibly on another stream); an event
+        // that was never recorded is complete by definition
+        MUB_CUDA(cudaEventSynchronize(s->events[b]), "stager_h2d: event sync");
+        char* stage = (char*)s->bufs[b];
+        const char* src = (const char*)src_h + off * (size_t)src_elem_bytes;
+        // split the chunk over the pool in 64-byte aligned parts
+        const size_t gran = 4096;
+        int parts = (int)((cnt + gran - 1) / gran);
+        if (parts > T) parts = T;
+        const size_t per = ((cnt + parts - 1) / parts + 15) & ~(size_t)15;
+        std::function<void(int)> fn = [&](int p) {
+            const size_t i0 = (size_t)p * per;
+            if (i0 >= cnt) { partial[p] = 0; return; }
+            const size_t m = cnt - i0 < per ? cnt - i0 : per;
+            if (narrow) {
+                partial[p] = narrow_hash_i64((int32_t*)stage + i0, (const int64_t*)src + i0, m, off + i0, hash_h != nullptr,
+                                             &overflow);
+            } else if (src_elem_bytes == 4) {
+                partial[p] = copy_hash_u32((uint32_t*)stage + i0, (const uint32_t*)src + i0, m, off + i0, hash_h != nullptr);
+            } else {
+                memcpy(stage + i0 * src_elem_bytes, src + i0 * src_elem_bytes, m * src_elem_bytes);
+                partial[p] = 0;
+            }
+        };
+        s->pool->run(fn, parts);
+        for (int p = 0; p < parts; ++p) hash += partial[p];
+        MUB_CUDA(cudaMemcpyAsync((char*)dst + off * dst_elem, stage, cnt * dst_elem, cudaMemcpyHostToDevice, st),
+                 "stager_h2d: cudaMemcpyAsync");
+        MUB_CUDA(cudaEventRecord(s->events[b], st), "stager_h2d: event record");
+    }
+    if (hash_h) *hash_h = hash;
+    if (overflow_h && overflow) *overflow_h = 1;
+    return 0;
+}
+
+// Device -> pageable host, n_bytes (multiple of 4 when a fingerprint is requested).  Synchronous with respect to
+// the host: returns when dst_h is complete.  hash_h: fingerprint of the downloaded 32-bit element stream.
+int mub_stager_d2h(void* handle, const void* src, void* dst_h, size_t n_bytes, uint64_t* hash_h, mub_stream_t stream) {
+    using namespace mub;
+    MUB_REQUIRE(handle != nullptr && ((mub::Stager*)handle)->n_bufs >= 2, "stager_d2h: stager has no staging buffers");
+    MUB_REQUIRE(!hash_h || (n_bytes % 4) == 0, "stager_d2h: fingerprint needs a multiple of 4 bytes");
+    if (hash_h) *hash_h = 0;
+    if (n_bytes == 0) return 0;
+    MUB_REQUIRE(src && dst_h, "stager_d2h: null pointer");
+    auto* s = (Stager*)handle;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t per_chunk = s->buf_bytes;
+    const size_t n_chunks = (n_bytes + per_chunk - 1) / per_chunk;
+    const int T = s->pool->size();
+    std::vector<uint64_t> partial(T, 0);
+    uint64_t hash = 0;
+    auto issue = [&](size_t c) -> int {
+        const int b = (int)(c % s->n_bufs);
+        const size_t off = c * per_chunk;
+        const size_t cnt = n_bytes - off < per_chunk ? n_bytes - off : per_chunk;
+        MUB_CUDA(cudaEventSynchronize(s->events[b]), "stager_d2h: event sync");   // earlier transfer still reading it?
+        MUB_CUDA(cudaMemcpyAsync(s->bufs[b], (const char*)src + off, cnt, cudaMemcpyDeviceToHost, st),
+                 "stager_d2h: cudaMemcpyAsync");
+        MUB_CUDA(cudaEventRecord(s->events[b], st), "stager_d2h: event record");
+        return 0;
+    };
+    for (size_t c = 0; c < n_chunks && c < (size_t)s->n_bufs; ++c)
+        if (int rc = issue(c)) return rc;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c % s->n_bufs);
+        const size_t off = c * per_chunk;
+        const size_t cnt = n_bytes - off < per_chunk ? n_bytes - off : per_chunk;
+        MUB_CUDA(cudaEventSynchronize(s->events[b]), "stager_d2h: event sync");
+        const char* stage = (const char*)s->bufs[b];
+        char* dst = (char*)dst_h + off;
+        const size_t gran = 16384;
+        int parts = (int)((cnt + gran - 1) / gran);
+        if (parts > T) parts = T;
+        const size_t per = ((cnt + parts - 1) / parts + 63) & ~(size_t)63;
+        std::function<void(int)> fn = [&](int p) {
+            const size_t i0 = (size_t)p * per;
+            if (i0 >= cnt) { partial[p] = 0; return; }
+            const size_t m = cnt - i0 < per ? cnt - i0 : per;
+            if (hash_h)
+                partial[p] = copy_hash_u32((uint32_t*)(dst + i0), (const uint32_t*)(stage + i0), m / 4, (off + i0) / 4, true);
+            else {
+                memcpy(dst + i0, stage + i0, m);
+                partial[p] = 0;
+            }
+        };
+        s->pool->run(fn, parts);
+        for (int p = 0; p < parts; ++p) hash += partial[p];
+        if (c + s->n_bufs < n_chunks)
+            if (int rc = issue(c + s->n_bufs)) return rc;
+    }
+    if (hash_h) *hash_h = hash;
+    return 0;
+}
+
+// Fingerprint of a host array without copying it: n_elems elements of 4 bytes, or of 8 bytes read as int64 and
+// narrowed to int32 (so that a host int64 index array and its int32 device twin have the same fingerprint).
+int mub_host_fingerprint(void* handle, const void* src_h, size_t n_elems, int32_t elem_bytes, uint64_t* hash_h) {
+    using namespace mub;
+    MUB_REQUIRE(handle && hash_h, "host_fingerprint: null pointer");
+    MUB_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "host_fingerprint: element size must be 4 or 8");
+    *hash_h = 0;
+    if (n_elems == 0) return 0;
+    MUB_REQUIRE(src_h, "host_fingerprint: null source");
+    auto* s = (Stager*)handle;
+    const int T = s->pool->size();
+    const size_t block = (size_t)1 << 20;                      // elements per work item
+    const size_t n_blocks = (n_elems + block - 1) / block;
+    std::vector<uint64_t> partial(T, 0);
+    std::atomic<size_t> next{0};
+    std::function<void(int)> fn = [&](int p) {
+        uint64_t h = 0;
+        for (;;) {
+            const size_t bi = next.fetch_add(1);
+            if (bi >= n_blocks) break;
+            const size_t i0 = bi * block;
+            const size_t m = n_elems - i0 < block ? n_elems - i0 : block;
+            h += hash_only((const char*)src_h + i0 * (size_t)elem_bytes, m, elem_bytes, i0);
+        }
+        partial[p] = h;
+    };
+    s->pool->run(fn, T);
+    uint64_t h = 0;
+    for (int p = 0; p < T; ++p) h += partial[p];
+    *hash_h = h;
+    return 0;
+}
+
+}  // extern "C"
+
+namespace mub {
+__global__ void __launch_bounds__(256)
+fingerprint_kernel(const uint32_t* __restrict__ src, int64_t n, unsigned long long* out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    uint64_t h = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        h += hash_term((uint32_t)ld_stream((const int*)src + i), (uint64_t)i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)h);
+}
+}  // namespace mub
+
+// Same fingerprint of a device array of n 32-bit elements, ACCUMULATED into *out (device uint64, zero it first).
+extern "C" int mub_device_fingerprint(const void* src, int64_t n, uint64_t* out, mub_stream_t stream) {
+    MUB_REQUIRE(n >= 0 && out, "device_fingerprint: bad argument");
+    if (n == 0) return 0;
+    MUB_REQUIRE(src, "device_fingerprint: null source");
+    int64_t want = (n + 255) / 256, cap = (int64_t)mub::sm_count() * 8;
+    int grid = (int)(want < cap ? want : cap);
+    mub::fingerprint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, n, (unsigned long long*)out);
+    return mub::check_launch("device_fingerprint");
+}

@@ -91,8 +91,9 @@ def test_float32_synth_vs_unmodified_reference(cuda):
 
 @pytest.mark.parametrize("dtype,rtol", [(np.float32, RTOL32), (np.float64, RTOL64)])
 def test_config0_shape_vs_oracle(cuda, dtype, rtol):
-    # BASELINE.json configs[0]: 10k x 30k, 5 % -- correctness only
-    X = generate_host(2000, 30000, 0.05, n_topics=16, seed=0).astype(dtype)
+    # BASELINE.json configs[0] at its real size: 10k cells x 30k peaks, 5 % (15 M nnz) -- correctness only
+    X = generate_host(10000, 30000, 0.05, n_topics=16, seed=0).astype(dtype)
+    assert X.shape == (10000, 30000) and 13e6 < X.nnz < 17e6
     ref = tfidf_ref(X)
     adata = SimpleAnnData(X.copy())
     mu.atac.pp.tfidf(adata)

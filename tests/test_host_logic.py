@@ -149,19 +149,18 @@ def test_k_beyond_separated_spectrum_is_reported_not_hidden():
     assert np.all(1 - lead < 1e-6)
 
 
-def test_resident_copy_checksum_sees_any_single_value_edit():
-    """lsi() reuses the device copy left by tfidf() only if every host value still matches it: the 64-bit
-    checksum of the raw bits must agree between the numpy and the torch implementation and change with any edit."""
-    import torch
+def test_resident_copy_fingerprint_sees_any_single_value_edit():
+    """lsi() reuses the device copy left by tfidf() only if every host element still matches what crossed the bus:
+    the staging engine's fingerprint must change with any single edit, at any length (tail handling)."""
     from muon_b200 import _device as d
-    for n in (0, 1, 7, 8, 9, 1_000_003):
+    pool = d.host_pool()
+    for n in (1, 7, 8, 9, 1_000_003):
         a = np.random.default_rng(n).standard_normal(n).astype(np.float32)
-        h = d._bits_checksum_host(a)
-        assert h == d._bits_checksum_device(torch.from_numpy(a))
-        if n:
-            b = a.copy()
-            b[n // 3] = np.nextafter(b[n // 3], np.float32(9))
-            assert d._bits_checksum_host(b) != h
+        h = pool.fingerprint(a)
+        b = a.copy()
+        b[n // 3] = np.nextafter(b[n // 3], np.float32(9))
+        assert pool.fingerprint(b) != h and pool.fingerprint(a.copy()) == h
+    assert pool.fingerprint(np.zeros(0, dtype=np.float32)) == 0
 
 
 def test_bench_onchip_roofline_arithmetic():
@@ -199,3 +198,76 @@ def test_neighbors_argument_errors_and_no_cpu_fallback():
             mu.pp.neighbors(SimpleMuData({k: v for k, v in ads.items() if k == "a"}))
         with pytest.raises(MuonB200Error):
             mu.tl.mofa(SimpleMuData({"y": SimpleAnnData(np.random.default_rng(1).normal(size=(20, 8)))}), n_factors=2)
+
+
+class HalfOperandOperator(ScipyOperator):
+    """ScipyOperator that also offers the product's low-precision mode: the dense operand of a product is rounded
+    to IEEE half after the same power-of-two scaling the CUDA path uses (muon_b200._device.HALF_SCALE)."""
+    lowp = True
+
+    def __init__(self, A):
+        super().__init__(A)
+        self.lowp_calls = 0
+
+    @staticmethod
+    def _round(M):
+        return (M.numpy() * np.float32(32768.0)).astype(np.float16).astype(np.float32) / np.float32(32768.0)
+
+    def av(self, V, lowp=False):
+        self.lowp_calls += int(lowp)
+        return torch.from_numpy(self.A @ (self._round(V) if lowp else V.numpy()))
+
+    def aty(self, Y, lowp=False):
+        self.lowp_calls += int(lowp)
+        return torch.from_numpy(self.At @ (self._round(Y) if lowp else Y.numpy()))
+
+
+@pytest.mark.parametrize("k,P,polish", [(20, 32, True), (30, 64, False)])
+def test_block_lanczos_half_precision_phase(k, P, polish):
+    """Two-phase schedule: half-precision operands until 1e-3, then fp32 from the Ritz vectors.  The result must
+    meet the same parity bar as the all-fp32 iteration, with most passes done in the cheap mode."""
+    X = tfidf_ref(generate_host(1500, 1200, 0.05, n_topics=12, seed=3)).astype(np.float32)
+    ref = lsi_ref(X, k + 1, dtype=np.float64)
+    s_next = ref["svalues"][k]
+    ref = {"svalues": ref["svalues"][:k], "U": ref["U"][:, :k], "LSI": ref["LSI"][:, :k]}
+    op = HalfOperandOperator(X)
+    U, s, V, info = truncated_svd(op, k, P, tol=1e-5, lowp_tol=1e-3, polish=polish)
+    assert info.converged and info.lowp_passes == op.lowp_calls > 0
+    assert info.lowp_passes >= info.passes // 2, (info.lowp_passes, info.passes)
+    out = compare_lsi({"svalues": s.numpy(), "U": U.numpy(), "LSI": V.numpy()}, ref, rtol=1e-4, s_next=s_next)
+    assert out["sigma_rel"] < 1e-5
+    # an operator without the low-precision mode ignores the request
+    U2, s2, V2, info2 = truncated_svd(ScipyOperator(X), k, P, tol=1e-5, lowp_tol=1e-3)
+    assert info2.lowp_passes == 0
+
+
+def test_host_fingerprint_pool_only():
+    """The staging engine's fingerprint on the host (thread pool only, no CUDA): independent of the thread count,
+    position dependent, and equal for an int64 array and its int32 narrowing."""
+    from muon_b200 import _device
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2**31 - 1, 3_000_001, dtype=np.int64)
+    h = [_device.Stager(pool_only=True, threads=t).fingerprint(a) for t in (1, 3, 8)]
+    assert h[0] == h[1] == h[2] == _device.Stager(pool_only=True, threads=2).fingerprint(a.astype(np.int32))
+    # the definition: sum_i (e_i + C1) * (i*C2 + C3) mod 2^64
+    C1, C2, C3, M = 0x9E3779B97F4A7C15, 0xD6E8FEB86659FD93, 0xA0761D6478BD642F, (1 << 64) - 1
+    small = [5, 0, 2**31 - 2, 77]
+    want = sum(((e + C1) & M) * ((i * C2 + C3) & M) for i, e in enumerate(small)) & M
+    assert _device.Stager(pool_only=True, threads=2).fingerprint(np.array(small, dtype=np.int32)) == want
+    b = a.copy()
+    b[[1, 2_999_999]] = b[[2_999_999, 1]]
+    assert _device.host_pool().fingerprint(b) != h[0]
+    f = rng.standard_normal(1000).astype(np.float32)
+    assert _device.host_pool().fingerprint(f) == _device.host_pool().fingerprint(f.view(np.uint32))
+
+
+def test_reference_arm_does_not_load_the_cuda_library():
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = ("import sys; sys.argv=['bench.py','--impl','reference','--sample-cells','300','--peaks','1500','--k','5',"
+            "'--steps','1','--warmup','1']; import runpy; runpy.run_path('bench.py', run_name='__main__');"
+            "assert 'libmuon_b200' not in open('/proc/self/maps').read(), 'reference arm loaded the CUDA library'")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert '"impl": "reference"' in out.stdout
