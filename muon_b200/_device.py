@@ -431,21 +431,27 @@ class TransposedPanels:
             torch.cuda.current_stream().wait_event(self.ready)
             self.ready = None
 
-    def spmm(self, Y: torch.Tensor, dynamic=True, half: bool = False) -> torch.Tensor:
-        """A^T Y accumulated panel by panel.  ``half``: round Y to IEEE half first (see ``spmm_h16``)."""
+    def spmm(self, Y: torch.Tensor, dynamic=True, half: bool = False, row_chunks: int = 1, on_chunk=None) -> torch.Tensor:
+        """A^T Y accumulated panel by panel.  ``half``: round Y to IEEE half first (see ``spmm_h16``).
+        ``row_chunks`` > 1 computes the result in that many blocks of output rows (peaks), each finished over all
+        panels before the next starts, and hands every finished block to ``on_chunk`` (the multi-GPU driver starts
+        its allreduce there, under the next block's product)."""
         self.wait()
-        out = None
+        d, P = self.shape[0], Y.shape[1]
         Yh = to_half_scaled(Y) if half else None
-        for r0, r1, T in self.panels:
-            if half:
-                if out is None:
-                    out = spmm_h16(T, Yh[r0:r1], dynamic=dynamic)
+        out = torch.empty((d, P), dtype=torch.float32, device=Y.device)
+        row_chunks = max(1, min(int(row_chunks), d))
+        cuts = [round(i * d / row_chunks) for i in range(row_chunks + 1)]
+        for j0, j1 in zip(cuts[:-1], cuts[1:]):
+            first = True
+            for r0, r1, T in self.panels:
+                if half:
+                    spmm_h16(T, Yh[r0:r1], out=out, accumulate=not first, dynamic=dynamic, rows=(j0, j1))
                 else:
-                    spmm_h16(T, Yh[r0:r1], out=out, accumulate=True, dynamic=dynamic)
-            elif out is None:
-                out = spmm(T, Y[r0:r1], dynamic=dynamic)
-            else:
-                spmm(T, Y[r0:r1], out=out, accumulate=True, dynamic=dynamic)
+                    spmm(T, Y[r0:r1], out=out, accumulate=not first, dynamic=dynamic, rows=(j0, j1))
+                first = False
+            if on_chunk is not None:
+                on_chunk(out[j0:j1])
         return out
 
 
@@ -461,7 +467,7 @@ def to_half_scaled(B: torch.Tensor, scale: float = HALF_SCALE) -> torch.Tensor:
 
 
 def spmm_h16(A, Bh: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False, dynamic=True,
-             scale: float = HALF_SCALE) -> torch.Tensor:
+             scale: float = HALF_SCALE, rows=None) -> torch.Tensor:
     """C[n x P] (+)= A @ (Bh / scale) with the dense operand stored as IEEE half (``to_half_scaled``): half the
     bytes per non-zero through the L2 -> L1 gather path that bounds the fp32 kernel; fp32 products and sums."""
     n, d = A.shape
@@ -471,17 +477,18 @@ def spmm_h16(A, Bh: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=Bh.device)
     counter = torch.zeros(1, dtype=torch.int64, device=Bh.device) if dynamic else None
+    j0, j1 = (0, n) if rows is None else rows          # output row range (indptr holds absolute offsets)
     if isinstance(A, DevicePairs):
-        call("mub_spmm_csrp_h16", ptr(A.indptr), ptr(A.pairs), n, d, ptr(Bh), P, ptr(out), 1 if accumulate else 0,
-             1.0 / scale, ptr(counter), stream_ptr())
-    else:
-        call("mub_spmm_csr_h16", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(Bh), P, ptr(out),
+        call("mub_spmm_csrp_h16", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(Bh), P, ptr(out) + 4 * P * j0,
              1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
+    else:
+        call("mub_spmm_csr_h16", ptr(A.indptr) + 8 * j0, ptr(A.indices), ptr(A.data), j1 - j0, d, ptr(Bh), P,
+             ptr(out) + 4 * P * j0, 1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
     return out
 
 
 def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate=False,
-         dynamic=True, algo: Optional[str] = None) -> torch.Tensor:
+         dynamic=True, algo: Optional[str] = None, rows=None) -> torch.Tensor:
     """K2/K3: C[n x P] (+)= A @ B[d x P];  P = B.shape[1] must be 32, 64 or 128.
 
     algo: "rowwarp" (v1: warp per row, B gathered from L2), "panel" (v2: B column panels staged in
@@ -492,10 +499,11 @@ def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accu
     if out is None:
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=B.device)
+    j0, j1 = (0, n) if rows is None else rows          # output row range (indptr holds absolute offsets)
     if isinstance(A, DevicePairs):
         counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
-        call("mub_spmm_csrp_f32", ptr(A.indptr), ptr(A.pairs), n, d, ptr(B), P, ptr(out), 1 if accumulate else 0,
-             ptr(counter), stream_ptr())
+        call("mub_spmm_csrp_f32", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(B), P, ptr(out) + 4 * P * j0,
+             1 if accumulate else 0, ptr(counter), stream_ptr())
         return out
     if algo is None:
         algo = os.environ.get("MUON_B200_SPMM", "auto")
@@ -508,8 +516,8 @@ def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accu
              1 if accumulate else 0, stream_ptr())
         return out
     counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
-    call("mub_spmm_csr_f32", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(B), P, ptr(out),
-         1 if accumulate else 0, ptr(counter), stream_ptr())
+    call("mub_spmm_csr_f32", ptr(A.indptr) + 8 * j0, ptr(A.indices), ptr(A.data), j1 - j0, d, ptr(B), P,
+         ptr(out) + 4 * P * j0, 1 if accumulate else 0, ptr(counter), stream_ptr())
     return out
 
 

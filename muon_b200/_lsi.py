@@ -42,6 +42,7 @@ from ._lib import phase
 class SvdInfo:
     passes: int = 0              # sparse passes over A or A^T
     lowp_passes: int = 0         # of which with the dense operand rounded to IEEE half
+    replica_repairs: int = 0     # multi-GPU: times the replicated d-space block had to be re-broadcast (expected 0)
     iterations: int = 0
     restarts: int = 0
     basis: int = 0
@@ -76,10 +77,20 @@ class CsrOperator:
             return self._dev.spmm(self.A, V, dynamic=False)
 
     def aty(self, Y, lowp: bool = False):
+        """A^T Y summed over the cell shards.  Multi-GPU: the product is computed in blocks of peaks and the
+        allreduce of block c runs (NCCL stream) under the SpMM of block c+1; only the last block's is exposed."""
         self.passes += 1
         with phase("lsi.spmm_aty"):
-            W = self.At.spmm(Y, dynamic=True, half=lowp)
-            return _dist.all_reduce_sum_(W)
+            if not _dist.is_distributed():
+                return self.At.spmm(Y, dynamic=True, half=lowp)
+            works = []
+            W = self.At.spmm(Y, dynamic=True, half=lowp, row_chunks=self.AR_CHUNKS,
+                             on_chunk=lambda blk: works.append(_dist.all_reduce_sum_async(blk)))
+            for w in works:
+                w.wait()
+            return W
+
+    AR_CHUNKS = int(os.environ.get("MUON_B200_AR_CHUNKS", "4"))
 
     def gram(self, Y, l):
         return self._dev.gram(Y, l, reduce=True)
@@ -247,9 +258,6 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
                 Qn, _ = _orth_against(Qn.contiguous(), Vall[:, :m], passes=1)
                 Qn, S2 = _qr_dspace(op, Qn, P)
                 Sj = (S2.to(f64) @ S1.to(f64))          # W = Qn Sj   (bj x bj)
-                if _dist.is_distributed():               # keep the replicated basis bit-identical
-                    Qn = _dist.broadcast_(Qn.contiguous())
-                    Sj = _dist.broadcast_(Sj.contiguous())
             # ---- Rayleigh-Ritz on the block-bidiagonal B (fp64, tiny) ---------------------
             with phase("lsi.ritz_svd"):
                 # Ritz triplets of the block-bidiagonal B through eigh(B^T B) in fp64 (several times cheaper
@@ -265,8 +273,23 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
                 res = torch.linalg.norm(Sj @ Xlast, dim=0) / sig[:kk].clamp_min(1e-300)
             else:
                 res = torch.zeros(kk, dtype=f64, device=dev)
-            if _dist.is_distributed():                   # one rank decides: control flow must not diverge
-                res = _dist.broadcast_(res.contiguous())
+            if _dist.is_distributed():
+                # The d-space basis is REPLICATED: every rank ran the same library calls on bit-identical input (the
+                # allreduced W), so Qn / Sj / res agree bit for bit without being exchanged.  One small MAX-allreduce
+                # carries both the stopping decision (control flow must not diverge) and a fingerprint of the new
+                # block that proves the replicas agree; only if they do not (never observed) rank 0's block is
+                # broadcast.  Round 1 broadcast Qn (51 MB), Sj and res every step: three sync points, now one.
+                if Sj is not None:
+                    chk = (Qn.sum(dtype=f64) + Sj.sum()).reshape(1)
+                else:
+                    chk = torch.zeros(1, dtype=f64, device=dev)
+                pack = _dist.all_reduce_max_(torch.cat([res, chk, -chk]))
+                res = pack[:kk]
+                if bool(pack[kk] != -pack[kk + 1]):
+                    info.replica_repairs += 1
+                    Qn = _dist.broadcast_(Qn.contiguous())
+                    Sj = _dist.broadcast_(Sj.contiguous())
+                    res = _dist.broadcast_((torch.linalg.norm(Sj @ Xlast, dim=0) / sig[:kk].clamp_min(1e-300)).contiguous())
             rmax = float(res.max())
             info.iterations += 1
             info.history.append(rmax)

@@ -77,7 +77,10 @@ class _View:
         self.n = cnt                                                # cells per group observed in this view (global)
         nn = cnt.clamp_min(1.0)[:, None]
         self.mean = s1 / nn                                        # intercepts per group, tools.py:283-286
-        mu = self.mean if center else torch.zeros_like(self.mean)
+        # center_groups=False still centres every feature, with its mean over ALL groups (mofapy2 process_data,
+        # [recalled]); with a single group the flag therefore changes nothing
+        mu = self.mean if center else (s1.sum(0) / cnt.sum().clamp_min(1.0))[None, :].expand(G, D).contiguous()
+        center = True
         ssq = (s2 - 2.0 * mu * s1 + cnt[:, None] * mu * mu).clamp_min(0)      # sum_n (y - mu)^2 per (g, d)
         tot = s1 - cnt[:, None] * mu                               # sum_n (y - mu)
         self.mu32 = mu.to(torch.float32).contiguous() if center else None
@@ -301,7 +304,8 @@ class MofaDevice:
             else:
                 Ea, Elna = torch.ones(K, dtype=f64, device=self.dev), torch.zeros(K, dtype=f64, device=self.dev)
             S0 = v.S[:, :K].to(f64)
-            W, WW, W2 = v.W[:, :K].to(f64), v.WW[:, :K].to(f64), v.What2[:, :K].to(f64)
+            W, WW = v.W[:, :K].to(f64), v.WW[:, :K].to(f64)
+            W2 = WW + (1.0 - S0) / Ea[None, :]     # spike branch at the current E[alpha] (see oracle/mofa_ref.py::elbo)
             S = S0.clamp(1e-300, 1.0)
             lp = -0.5 * np.log(two_pi) + 0.5 * Elna[None, :] - 0.5 * Ea[None, :] * W2
             Sd = S0.clamp_min(1e-300)

@@ -58,7 +58,9 @@ def preprocess(views, center=True, scale_views=False):
     out, means, scales = [], [], []
     for Y in views:
         Y = np.asarray(Y.todense() if hasattr(Y, "todense") else Y, dtype=np.float64)  # tools.py:117-141
-        mu = Y.mean(axis=0) if center else np.zeros(Y.shape[1])
+        # mofapy2's process_data centres gaussian views in either setting of center_groups: per group if set,
+        # else with the mean over all samples ([recalled]; with one group both are the same mean)
+        mu = Y.mean(axis=0)
         Yc = Y - mu
         sc = float(Yc.std()) if scale_views else 1.0
         out.append(Yc / sc)
@@ -164,7 +166,11 @@ def elbo(st: MofaState, N, ard_weights=True, ard_factors=True, spikeslab=True):
         S = np.clip(st.S[m], 1e-300, 1.0)
         # E ln p(what|alpha) + entropy of q(what|s) (both branches)
         D = S.shape[0]
-        mW2 = st.What2[m]
+        # q(what | s=0) = N(0, 1/E[alpha]) is taken at the CURRENT E[alpha] in both terms that contain it (the
+        # prior expectation below and the entropy), i.e. the bound is maximised over that free variance; What2
+        # (frozen at the W update) only feeds the AlphaW update.  Checked term by term against a dense evaluation
+        # in tests/test_oracle_mofa.py::test_elbo_equals_bruteforce_dense_evaluation.
+        mW2 = st.WW[m] + (1.0 - st.S[m]) / Ea[None, :]
         lp = -0.5 * np.log(2 * np.pi) + 0.5 * Elna[None, :] - 0.5 * Ea[None, :] * mW2
         var1 = np.where(st.S[m] > 0, st.WW[m] / np.maximum(st.S[m], 1e-300) - (st.W[m] / np.maximum(st.S[m], 1e-300)) ** 2, 1.0)
         var1 = np.maximum(var1, 1e-300)
@@ -273,9 +279,22 @@ def mofa_ref(views, n_factors=10, n_iterations=1000, center=True, scale_views=Fa
 # ======================================================================================================
 def mofa_ref_general(views, groups=None, n_factors=10, n_iterations=1000, center_groups=True, scale_views=False,
                      scale_groups=False, ard_weights=True, ard_factors=True, spikeslab_weights=True,
-                     convergence_mode="fast", seed=1, Z0=None, sort_factors=True, check_convergence=True):
+                     convergence_mode="fast", seed=1, Z0=None, sort_factors=True, check_convergence=True,
+                     likelihoods=None):
     """``views``: list of N x D_m float arrays with NaN = missing; ``groups``: length-N array of group labels
-    (None = one group).  Returns Z, W, variance[view] -> array (G x K, %), elbo, ..."""
+    (None = one group).  Returns Z, W, variance[view] -> array (G x K, %), elbo, ...
+
+    ``likelihoods``: per view "gaussian" (default), "poisson" or "bernoulli" -- what mofapy2's
+    ``guess_likelihoods`` picks for integer / binary data when muon passes ``likelihoods=None``
+    (muon/_core/tools.py:272-280).  Non-gaussian views follow Seeger & Bouchard (AISTATS 2012) as used by MOFA
+    (Argelaguet et al. 2018, Appendix 'Non-gaussian likelihoods') [recalled from mofapy2's Poisson_PseudoY /
+    Bernoulli_PseudoY / Tau_Seeger nodes, not checkable here]: each iteration starts by replacing the view with
+    gaussian PSEUDO-DATA around zeta = E[Z]E[W]^T at a FIXED precision kappa_d,
+        poisson   : rate(z) = ln(1+e^z),  yhat = zeta - sigmoid(zeta) (1 - y / rate(zeta)) / kappa,  kappa_d = 1/4 + 0.17 max_n y_nd
+        bernoulli : yhat = zeta - (sigmoid(zeta) - y) / kappa,                                        kappa   = 1/4
+    after which W and Z are updated exactly as for a gaussian view with tau = kappa; there is no Tau update,
+    no centring and no scaling for such a view, and its ELBO term is the likelihood at zeta (sum y ln rate - rate,
+    resp. sum y zeta - ln(1+e^zeta))."""
     Ys = [np.array(Y.todense() if hasattr(Y, "todense") else Y, dtype=np.float64) for Y in views]
     N = Ys[0].shape[0]
     M = len(Ys)
@@ -283,16 +302,28 @@ def mofa_ref_general(views, groups=None, n_factors=10, n_iterations=1000, center
     glab = np.zeros(N, dtype=np.int64) if groups is None else np.unique(np.asarray(groups), return_inverse=True)[1]
     G = int(glab.max()) + 1
     gsel = [glab == g for g in range(G)]
+    liks = ["gaussian"] * M if likelihoods is None else ([likelihoods] * M if isinstance(likelihoods, str) else list(likelihoods))
+    assert all(l in ("gaussian", "poisson", "bernoulli") for l in liks), liks
+    obs, kappa = [None] * M, [None] * M
     masks, means, scales = [], [], []
     for m in range(M):
         mask = ~np.isnan(Ys[m])
         Y = np.where(mask, Ys[m], 0.0)
+        if liks[m] != "gaussian":                            # no centring / scaling; fixed precision kappa
+            obs[m] = Y.copy()
+            kappa[m] = 0.25 + 0.17 * Y.max(0) if liks[m] == "poisson" else np.full(Y.shape[1], 0.25)
+            Ys[m] = Y
+            masks.append(mask)
+            means.append(np.zeros((G, Y.shape[1])))
+            scales.append(np.ones(G))
+            continue
         mu = np.zeros((G, Y.shape[1]))
+        mu_all = Y.sum(0) / np.maximum(mask.sum(0), 1)        # center_groups=False: mean over all groups ([recalled])
         for g in range(G):
             cnt = mask[gsel[g]].sum(0)
             mu[g] = Y[gsel[g]].sum(0) / np.maximum(cnt, 1)
-            if center_groups:
-                Y[gsel[g]] -= mu[g] * mask[gsel[g]]
+        for g in range(G):
+            Y[gsel[g]] -= (mu[g] if center_groups else mu_all) * mask[gsel[g]]
         sc = np.ones(G)
         if scale_views:
             sc[:] = np.sqrt((Y ** 2).sum() / mask.sum() - (Y.sum() / mask.sum()) ** 2)
@@ -317,10 +348,24 @@ def mofa_ref_general(views, groups=None, n_factors=10, n_iterations=1000, center
     alphaW = [(np.ones(K), np.ones(K)) for _ in dims]
     alphaZ = (np.ones((G, K)), np.ones((G, K)))
     theta = [(np.ones(K), np.full(K, 1e-8)) for _ in dims]
-    tau = [(np.ones((G, D)), np.ones((G, D))) for D in dims]
+    tau = [(np.ones((G, D)), np.ones((G, D))) if liks[m] == "gaussian" else
+           (np.tile(kappa[m], (G, 1)), np.ones((G, D))) for m, D in enumerate(dims)]
     tol = TOLERANCE[convergence_mode]
     elbos, converged, it = [], False, -1
+
+    def _softplus(x):
+        return np.logaddexp(0.0, x)
+
     for it in range(n_iterations):
+        for m in range(M):                                   # ---- Y: pseudo-data of the non-gaussian views
+            if liks[m] == "gaussian":
+                continue
+            zeta = Z @ W[m].T
+            if liks[m] == "poisson":
+                rate = np.maximum(_softplus(zeta), 1e-300)
+                Ys[m] = np.where(masks[m], zeta - expit(zeta) * (1.0 - obs[m] / rate) / kappa[m][None, :], 0.0)
+            else:
+                Ys[m] = np.where(masks[m], zeta - (expit(zeta) - obs[m]) / kappa[m][None, :], 0.0)
         ZZd = Z ** 2 + Zvar
         for m in range(M):
             Etau = (tau[m][0] / tau[m][1])[glab] * masks[m]                     # N x D, 0 where missing
@@ -359,6 +404,8 @@ def mofa_ref_general(views, groups=None, n_factors=10, n_iterations=1000, center
             alphaZ = (np.stack([np.full(K, A0 + 0.5 * gsel[g].sum()) for g in range(G)]),
                       np.stack([B0 + 0.5 * ZZd[gsel[g]].sum(0) for g in range(G)]))
         for m in range(M):
+            if liks[m] != "gaussian":
+                continue
             E2 = (Ys[m] - Z @ W[m].T) ** 2 + ZZd @ WW[m].T - (Z ** 2) @ (W[m] ** 2).T
             ta = np.stack([A0 + 0.5 * masks[m][gsel[g]].sum(0) for g in range(G)])
             tb = np.stack([B0 + 0.5 * (E2[gsel[g]] * masks[m][gsel[g]]).sum(0) for g in range(G)])
@@ -366,13 +413,21 @@ def mofa_ref_general(views, groups=None, n_factors=10, n_iterations=1000, center
         # ---- ELBO (same terms as ``elbo`` above, per group / per cell) ---------------------------------
         tot = 0.0
         for m in range(M):
-            Etau, Elntau = _E_gamma(tau[m])
-            nmg = np.stack([masks[m][gsel[g]].sum(0) for g in range(G)])
-            tot += float(np.sum(0.5 * nmg * (Elntau - np.log(2 * np.pi)) - Etau * (tau[m][1] - B0)))
-            tot += _kl_gamma(tau[m], A0, B0)
+            if liks[m] == "gaussian":
+                Etau, Elntau = _E_gamma(tau[m])
+                nmg = np.stack([masks[m][gsel[g]].sum(0) for g in range(G)])
+                tot += float(np.sum(0.5 * nmg * (Elntau - np.log(2 * np.pi)) - Etau * (tau[m][1] - B0)))
+                tot += _kl_gamma(tau[m], A0, B0)
+            else:
+                zeta = Z @ W[m].T
+                if liks[m] == "poisson":
+                    rate = np.maximum(_softplus(zeta), 1e-300)
+                    tot += float(np.sum(np.where(masks[m], obs[m] * np.log(rate) - rate, 0.0)))
+                else:
+                    tot += float(np.sum(np.where(masks[m], obs[m] * zeta - _softplus(zeta), 0.0)))
             Ea, Elna = _E_gamma(alphaW[m]) if ard_weights else (np.ones(K), np.zeros(K))
             Sc = np.clip(S[m], 1e-300, 1.0)
-            lp = -0.5 * np.log(2 * np.pi) + 0.5 * Elna[None, :] - 0.5 * Ea[None, :] * What2[m]
+            lp = -0.5 * np.log(2 * np.pi) + 0.5 * Elna[None, :] - 0.5 * Ea[None, :] * (WW[m] + (1.0 - S[m]) / Ea[None, :])
             var1 = np.maximum(np.where(S[m] > 0, WW[m] / np.maximum(S[m], 1e-300) - (W[m] / np.maximum(S[m], 1e-300)) ** 2, 1.0), 1e-300)
             ent = Sc * 0.5 * np.log(2 * np.pi * np.e * var1) + (1 - Sc) * 0.5 * np.log(2 * np.pi * np.e / Ea[None, :])
             tot += float(np.sum(lp + ent))
