@@ -160,6 +160,19 @@ int mub_mofa_tau_f32(const float* Praw, const float* mu, const double* zsum, dou
                      const double* ssq, const float* W, const float* WW, double b0, double* b_out, int64_t D,
                      int32_t ld, int32_t K, mub_stream_t stream);
 
+/* Non-gaussian likelihoods (mofapy2 guesses "poisson" for integer and "bernoulli" for binary views when muon
+ * passes likelihoods=None, muon/_core/tools.py:272-280): Seeger pseudo-data of a DENSE row-major view around
+ * zeta = E[Z] E[W]^T at fixed precision kappa[D] (restated in oracle/mofa_ref.py::mofa_ref_general).
+ * kind: 1 = poisson  yhat = zeta - sigmoid(zeta) (1 - y / ln(1+e^zeta)) / kappa_d
+ *       2 = bernoulli yhat = zeta - (sigmoid(zeta) - y) / kappa_d
+ * mofa_pseudo overwrites zeta[n_rows x D] with yhat; mofa_loglik ACCUMULATES sum ln p(y | zeta) into *out (device
+ * double; poisson: y ln rate - rate, bernoulli: y zeta - ln(1+e^zeta)). */
+int mub_mofa_pseudo_f32(float* zeta, const float* obs, const float* kappa, int64_t n_rows, int32_t D, int32_t kind,
+                        mub_stream_t stream);
+int mub_mofa_loglik_f32(const float* zeta, const float* obs, int64_t n_rows, int32_t D, int32_t kind, double* out,
+                        mub_stream_t stream);
+
+
 /* ---- exact k-nearest neighbours (groundwork for the WNN row, muon/_core/preproc.py:520-528: the reference asks
  * umap's NN-descent for n_multineighbors+1 = 201 neighbours per cell and modality; this search is exact).
  * For every row of X[nq x ld] (d meaningful columns) the k nearest rows of Y[nc x ld] in Euclidean distance,

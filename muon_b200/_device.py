@@ -736,5 +736,8 @@ def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Opti
         # st & 2: error band too crowded for some query -> exact SIMT kernel below
     elif algo not in ("simt", "tc"):
         raise ValueError(f"unknown kNN algorithm {algo!r}")
+    if k > 320:
+        raise NotImplementedError(f"knn_l2: k = {k} > 320 needs the tensor-core path, which declined this input (more than 896 "
+                                  "points inside a query's TF32 error band, or d > 128); the fp32 SIMT kernel supports k <= 320")
     call("mub_knn_l2_f32", ptr(X), nq, ptr(Y), Y.shape[0], d, d, k, ptr(idx), ptr(dist), stream_ptr())
     return idx, dist

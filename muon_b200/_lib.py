@@ -42,6 +42,8 @@ SIGNATURES = {
     "mub_mofa_update_w_f32": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],
     "mub_mofa_update_z_f32": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, vp],
     "mub_mofa_tau_f32": [vp, vp, vp, f64, vp, vp, vp, vp, f64, vp, i64, i32, i32, vp],
+    "mub_mofa_pseudo_f32": [vp, vp, vp, i64, i32, i32, vp],
+    "mub_mofa_loglik_f32": [vp, vp, i64, i32, i32, vp, vp],
     "mub_knn_l2_f32": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp],
     "mub_knn_l2_tc_f32": [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, C.c_size_t, vp, vp],
     "mub_wnn_bandwidth_f32": [vp, vp, vp, vp, vp, i64, i32, i32, i32, f64, vp, vp, vp, i64, vp, i32, i32, vp],

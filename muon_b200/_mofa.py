@@ -48,29 +48,89 @@ class _Block:
     def take(self, Z):                                   # rows of Z belonging to this block (contiguous n x ld)
         return Z[self.lo:self.hi] if self.rows is None else Z.index_select(0, self.rows)
 
+    def aty(self, Zb):                                   # Y_b^T Z_b  (D x ld): transposed sparse pass
+        return self.At.spmm(Zb.contiguous(), dynamic=True)
+
+    def add_av(self, Q, tw):                             # Q[rows of the block] += Y_b (tau * W)
+        if self.rows is None:
+            _device.spmm(self.A, tw, out=Q[self.lo:self.hi], accumulate=True, dynamic=False)
+        else:
+            Q.index_add_(0, self.rows, _device.spmm(self.A, tw, dynamic=False))
+
+    def moments(self, D, dev):
+        """per-feature sum and sum of squares over the block's cells (fp64), from the transposed panels"""
+        s1, s2 = torch.zeros(D, dtype=f64, device=dev), torch.zeros(D, dtype=f64, device=dev)
+        self.At.wait()
+        for (_, _, T) in self.At.panels:
+            t1, t2 = torch.empty(D, dtype=f64, device=dev), torch.empty(D, dtype=f64, device=dev)
+            if isinstance(T, _device.DevicePairs):
+                call("mub_csrp_row_stats_f32", ptr(T.indptr), ptr(T.pairs), D, ptr(t1), ptr(t2), stream_ptr())
+            else:
+                call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
+            s1 += t1
+            s2 += t2
+        return s1, s2
+
+
+class _DenseBlock:
+    """One (view, group) block of a NON-gaussian view: the observations as a dense row-major fp32 matrix and the
+    Seeger pseudo-data that stand in for them (dense by construction: zeta = E[Z] E[W]^T is).  The contractions
+    are GEMMs (cuBLAS via torch); the elementwise passes are csrc/mofa_pseudo.cu."""
+
+    def __init__(self, obs: torch.Tensor, rows, lo: int, hi: int):
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.dim() == 2
+        self.obs, self.Y = obs, torch.zeros_like(obs)
+        self.rows, self.lo, self.hi = rows, lo, hi
+        self.n_local = obs.shape[0]
+
+    def take(self, Z):
+        return Z[self.lo:self.hi] if self.rows is None else Z.index_select(0, self.rows)
+
+    def aty(self, Zb):
+        return self.Y.T @ Zb
+
+    def add_av(self, Q, tw):
+        if self.rows is None:
+            Q[self.lo:self.hi].addmm_(self.Y, tw)
+        else:
+            Q.index_add_(0, self.rows, self.Y @ tw)
+
 
 class _View:
     """One modality: blocks per group, per-(group, feature) moments, variational state of W / alpha / theta / tau."""
 
-    def __init__(self, blocks, D: int, K: int, ld: int, center: bool, scale_views: bool, scale_groups: bool, dev):
+    def __init__(self, blocks, D: int, K: int, ld: int, center: bool, scale_views: bool, scale_groups: bool, dev,
+                 lik: str = "gaussian"):
         self.blocks, self.D, self.G = blocks, D, len(blocks)
+        self.lik = lik
+        self.kind = {"gaussian": 0, "poisson": 1, "bernoulli": 2}[lik]
         G = self.G
         s1 = torch.zeros((G, D), dtype=f64, device=dev)
         s2 = torch.zeros((G, D), dtype=f64, device=dev)
         cnt = torch.zeros(G, dtype=f64, device=dev)
+        mx = torch.zeros(D, dtype=torch.float32, device=dev)
         for g, b in enumerate(blocks):
             cnt[g] = b.n_local
             if b.n_local == 0:
                 continue
-            b.At.wait()
-            for (_, _, T) in b.At.panels:
-                t1, t2 = torch.empty(D, dtype=f64, device=dev), torch.empty(D, dtype=f64, device=dev)
-                if isinstance(T, _device.DevicePairs):
-                    call("mub_csrp_row_stats_f32", ptr(T.indptr), ptr(T.pairs), D, ptr(t1), ptr(t2), stream_ptr())
-                else:
-                    call("mub_csr_row_stats_f32", ptr(T.indptr), ptr(T.data), D, ptr(t1), ptr(t2), stream_ptr())
-                s1[g] += t1
-                s2[g] += t2
+            if self.kind == 0:
+                s1[g], s2[g] = b.moments(D, dev)
+            else:
+                mx = torch.maximum(mx, b.obs.max(0).values)
+        if self.kind != 0:
+            # non-gaussian view: no centring, no scaling, precision fixed at Seeger's bound (oracle/mofa_ref.py)
+            _dist.all_reduce_sum_(cnt)
+            _dist.all_reduce_max_(mx)
+            self.n = cnt
+            self.mean = torch.zeros((G, D), dtype=f64, device=dev)
+            self.mu32, self.mu64 = None, self.mean
+            self.inv_scale = torch.ones(G, dtype=f64, device=dev)
+            self.ssq = torch.zeros((G, D), dtype=f64, device=dev)          # of the pseudo-data: refreshed every iteration
+            kappa = (0.25 + 0.17 * mx.to(f64)) if self.kind == 1 else torch.full((D,), 0.25, dtype=f64, device=dev)
+            self.kappa32 = kappa.to(torch.float32).contiguous()
+            self._init_state(K, ld, dev)
+            self.tau = (kappa[None, :].expand(G, D).contiguous(), torch.ones((G, D), dtype=f64, device=dev))
+            return
         _dist.all_reduce_sum_(s1)
         _dist.all_reduce_sum_(s2)
         _dist.all_reduce_sum_(cnt)
@@ -96,6 +156,10 @@ class _View:
             inv = torch.where(var > 0, 1.0 / torch.sqrt(var.clamp_min(1e-300)), torch.ones_like(var))
         self.inv_scale = inv.contiguous()
         self.ssq = (ssq * (inv ** 2)[:, None]).contiguous()
+        self._init_state(K, ld, dev)
+
+    def _init_state(self, K, ld, dev):
+        D, G = self.D, self.G
         z = lambda: torch.zeros((D, ld), dtype=torch.float32, device=dev)  # noqa: E731
         self.W, self.WW, self.S, self.What2 = z(), z(), z(), z()
         self.S[:, :K] = 1.0
@@ -153,8 +217,9 @@ class MofaDevice:
     """
 
     def __init__(self, blocks, dims, group_ranges, n_groups_total, cls, K, Z0, center=True, scale_views=False,
-                 scale_groups=False, ard_weights=True, ard_factors=True, spikeslab_weights=True):
+                 scale_groups=False, ard_weights=True, ard_factors=True, spikeslab_weights=True, likelihoods=None):
         self.K = int(K)
+        self.liks = ["gaussian"] * len(blocks) if likelihoods is None else list(likelihoods)
         if K > 64:
             raise NotImplementedError("n_factors > 64 is not supported yet")
         self.ld = ld = _device.pad_width(K)
@@ -180,11 +245,12 @@ class MofaDevice:
             bl = []
             for g in range(self.G):
                 A, rows = blocks[m][g]
-                if isinstance(rows, tuple):
-                    bl.append(_Block(A, None, rows[0], rows[1], ld))
-                else:
-                    bl.append(_Block(A, rows, 0, 0, ld))
-            self.views.append(_View(bl, dims[m], K, ld, center, scale_views, scale_groups, dev))
+                r, lo, hi = (None, rows[0], rows[1]) if isinstance(rows, tuple) else (rows, 0, 0)
+                if self.liks[m] == "gaussian":
+                    bl.append(_Block(A, r, lo, hi, ld))
+                else:                                     # A: dense fp32 observations (n_b x D) on the device
+                    bl.append(_DenseBlock(A, r, lo, hi))
+            self.views.append(_View(bl, dims[m], K, ld, center, scale_views, scale_groups, dev, self.liks[m]))
         self.Z = torch.zeros((self.n_local, ld), dtype=torch.float32, device=dev)
         self.Z[:, :K] = Z0.to(dev, torch.float32)
         self.zvar = torch.ones((self.C, K), dtype=f64, device=dev)
@@ -206,7 +272,7 @@ class MofaDevice:
                     Zb = b.take(self.Z)
                     ZZ = _device.gram(Zb, K, reduce=False)
                     zs = Zb[:, :K].sum(0, dtype=f64)
-                    P = b.At.spmm(Zb.contiguous(), dynamic=True)
+                    P = b.aty(Zb.contiguous())
                 else:
                     ZZ = torch.zeros((K, K), dtype=f64, device=self.dev)
                     zs = torch.zeros(K, dtype=f64, device=self.dev)
@@ -234,6 +300,10 @@ class MofaDevice:
         K, ld, st, G, M, C = self.K, self.ld, stream_ptr(), self.G, self.M, self.C
         ard_w, ard_f, ss = self.opts
         onesK = torch.ones(K, dtype=f64, device=self.dev)
+        # ---- Y: pseudo-data of the non-gaussian views (and the statistics that depend on them) -------------------
+        for v in self.views:
+            if v.kind != 0:
+                self._pseudo(v)
         # ---- W ----------------------------------------------------------------------------------------
         for v in self.views:
             Etau = _E_gamma(v.tau)[0].to(torch.float32).contiguous()              # G x D
@@ -252,10 +322,7 @@ class MofaDevice:
             for g, b in enumerate(v.blocks):
                 tw = (v.W * (v.Etau32[g] * v.inv_scale[g].to(torch.float32))[:, None]).contiguous()   # D x ld operand
                 if b.n_local > 0:
-                    if b.rows is None:
-                        _device.spmm(b.A, tw, out=Q[b.lo:b.hi], accumulate=True, dynamic=False)
-                    else:
-                        Q.index_add_(0, b.rows, _device.spmm(b.A, tw, dynamic=False))
+                    b.add_av(Q, tw)
                 qs = (v.mu64[g][:, None] * tw[:, :K].to(f64)).sum(0) if v.mu32 is not None else 0.0
                 gw = _device.gram(v.W, K, weights=v.Etau32[g].contiguous(), reduce=False)
                 cw = v.Etau32[g].to(f64) @ v.WW[:, :K].to(f64)
@@ -281,6 +348,8 @@ class MofaDevice:
             self.alphaZ = ((A0 + 0.5 * self.Ng)[:, None].expand(G, K).contiguous(), B0 + 0.5 * self.Ez2)
         # ---- Tau ----------------------------------------------------------------------------------------
         for v in self.views:
+            if v.kind != 0:                                  # Seeger bound: the precision is a constant
+                continue
             b = torch.empty((G, v.D), dtype=f64, device=self.dev)
             for g in range(G):
                 call("mub_mofa_tau_f32", ptr(v.P[g]), ptr(v.mu32[g]) if v.mu32 is not None else None, ptr(v.zsum[g]),
@@ -289,6 +358,36 @@ class MofaDevice:
             v.tau = ((A0 + 0.5 * v.n)[:, None].expand(G, v.D).contiguous(), b)
         self.elbo.append(self._elbo())
 
+    def _pseudo(self, v):
+        """Seeger pseudo-data of a non-gaussian view around zeta = E[Z] E[W]^T (csrc/mofa_pseudo.cu), then the
+        statistics of the view that depend on them: P = Yhat^T E[Z] and sum Yhat^2 per feature."""
+        K, st = self.K, stream_ptr()
+        Wk = v.W[:, :K].contiguous()
+        for g, b in enumerate(v.blocks):
+            if b.n_local == 0:
+                v.P[g].zero_()
+                v.ssq[g].zero_()
+                continue
+            Zb = b.take(self.Z).contiguous()
+            torch.matmul(Zb[:, :K], Wk.T, out=b.Y)
+            call("mub_mofa_pseudo_f32", ptr(b.Y), ptr(b.obs), ptr(v.kappa32), b.n_local, v.D, v.kind, st)
+            v.P[g] = b.aty(Zb)
+            v.ssq[g] = (b.Y * b.Y).sum(0, dtype=f64)
+        _dist.all_reduce_sum_(v.P)
+        _dist.all_reduce_sum_(v.ssq)
+
+    def _loglik(self, v):
+        """sum over the observed entries of ln p(y | zeta) at zeta = E[Z] E[W]^T (the ELBO term of a non-gaussian view)"""
+        K, st = self.K, stream_ptr()
+        acc = torch.zeros(1, dtype=f64, device=self.dev)
+        Wk = v.W[:, :K].contiguous()
+        for b in v.blocks:
+            if b.n_local == 0:
+                continue
+            zeta = b.take(self.Z)[:, :K].contiguous() @ Wk.T
+            call("mub_mofa_loglik_f32", ptr(zeta), ptr(b.obs), b.n_local, v.D, v.kind, ptr(acc), st)
+        return float(_dist.all_reduce_sum_(acc)[0])
+
     def _elbo(self):
         """Same expression as oracle/mofa_ref.py (tau trick; valid right after the Tau update)."""
         K, G, M = self.K, self.G, self.M
@@ -296,9 +395,12 @@ class MofaDevice:
         total = 0.0
         two_pi = 2.0 * np.pi
         for v in self.views:
-            Etau, Elntau = _E_gamma(v.tau)
-            total += float((0.5 * v.n[:, None] * (Elntau - np.log(two_pi)) - Etau * (v.tau[1] - B0)).sum())
-            total += _kl_gamma(v.tau, A0, B0)
+            if v.kind == 0:
+                Etau, Elntau = _E_gamma(v.tau)
+                total += float((0.5 * v.n[:, None] * (Elntau - np.log(two_pi)) - Etau * (v.tau[1] - B0)).sum())
+                total += _kl_gamma(v.tau, A0, B0)
+            else:
+                total += self._loglik(v)
             if ard_w:
                 Ea, Elna = _E_gamma(v.alpha)
             else:
@@ -373,13 +475,14 @@ def _train(model, n_iterations, convergence_mode, check_convergence, sort_factor
 
 def run_mofa_device(views, n_factors, n_iterations, n_total, Z0, center=True, scale_views=False, ard_weights=True,
                     ard_factors=True, spikeslab_weights=True, convergence_mode="fast", check_convergence=True,
-                    sort_factors=True, verbose=False):
-    """One group, every cell observed in every view (the benchmark case).  ``views``: DeviceCSR per modality
-    (this rank's cells).  Returns dict(Z, W (list), variance (list of K-vectors), elbo, iterations, converged)."""
+                    sort_factors=True, verbose=False, likelihoods=None):
+    """One group, every cell observed in every view (the benchmark case).  ``views``: per modality a DeviceCSR
+    (gaussian) or a dense fp32 device tensor (poisson / bernoulli, see ``likelihoods``) of this rank's cells.
+    Returns dict(Z, W (list), variance (list of K-vectors), elbo, iterations, converged)."""
     n_local = views[0].shape[0]
     blocks = [[(A, (0, n_local))] for A in views]
     model = MofaDevice(blocks, [A.shape[1] for A in views], [(0, n_local)], [n_total], None, n_factors, Z0, center,
-                       scale_views, False, ard_weights, ard_factors, spikeslab_weights)
+                       scale_views, False, ard_weights, ard_factors, spikeslab_weights, likelihoods)
     res = _train(model, n_iterations, convergence_mode, check_convergence, sort_factors, verbose)
     res["variance"] = [x[0] for x in res["variance"]]
     res["intercepts"] = [x[0] for x in res["intercepts"]]
@@ -393,6 +496,51 @@ def _to_device_view(X):
         return X if X.data.dtype == torch.float32 else X.with_data(X.data.to(torch.float32))
     Xs = X.tocsr() if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
     return _device.DeviceCSR.from_scipy(Xs, dtype=np.float32)
+
+
+def _guess_likelihood(X) -> str:
+    """mofapy2's ``guess_likelihoods`` (reached from muon/_core/tools.py:272-280) on one view: bernoulli if every
+    value is 0 or 1, poisson if every value is an integer, else gaussian.  Implicit zeros of a sparse matrix are
+    integers, so only the stored values need looking at (all of them, not a sample)."""
+    if isinstance(X, _device.DeviceCSR):
+        vals = X.data
+        if vals.numel() == 0:
+            return "bernoulli"
+        if not bool((vals == vals.round()).all()):
+            return "gaussian"
+        return "bernoulli" if bool(((vals == 0) | (vals == 1)).all()) else "poisson"
+    vals = X.data if hasattr(X, "data") and not isinstance(X, np.ndarray) else np.asarray(X).ravel()
+    vals = np.asarray(vals)
+    vals = vals[~np.isnan(vals)] if vals.dtype.kind == "f" else vals
+    if vals.size and not np.all(vals == np.round(vals)):
+        return "gaussian"
+    return "bernoulli" if np.all((vals == 0) | (vals == 1)) else "poisson"
+
+
+def _check_dense_fits(name, shape, lik, dev):
+    """Non-gaussian views need dense N x D pseudo-data (observations + pseudo-data + zeta: 12 B per element)."""
+    need = 12.0 * shape[0] * shape[1]
+    free = torch.cuda.mem_get_info(dev)[0]
+    if need > 0.6 * free:
+        raise NotImplementedError(
+            f"view '{name}' ({shape[0]} x {shape[1]}) was given / guessed the {lik} likelihood, whose pseudo-data are dense by "
+            f"construction: {need / 2**30:.0f} GiB needed, {free / 2**30:.0f} GiB free on the device (the reference densifies "
+            "every view and cannot run this size either).  Pass likelihoods='gaussian' for normalised data, or subset.")
+
+
+def _to_dense_device(X, dev) -> torch.Tensor:
+    """Any matrix -> dense row-major fp32 tensor on the device (the observations of a non-gaussian view)."""
+    import scipy.sparse as sp
+    if isinstance(X, torch.Tensor):
+        return X.to(dev, torch.float32).contiguous()
+    if isinstance(X, _device.DeviceCSR):
+        t = torch.sparse_csr_tensor(X.indptr, X.indices.to(torch.int64), X.data.to(torch.float32), size=X.shape, device=dev)
+        return t.to_dense().contiguous()
+    arr = X.toarray() if sp.issparse(X) else np.asarray(X)
+    if np.isnan(arr).any():
+        raise NotImplementedError("missing values (NaN) inside a non-gaussian view are not supported; drop the cells "
+                                  "from the view and use use_obs='union'")
+    return torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(dev)
 
 
 def mofa(
@@ -451,8 +599,12 @@ def mofa(
         raise TypeError("Expected an MuData object")
 
     if use_var and (not hasattr(data.var, "columns") or use_var not in data.var.columns):
-        warn(f"There is no column {use_var} in the provided object")     # tools.py:438-440
-        use_var = None
+        # mudata lifts a .var column shared by every modality into mdata.var on update(); the test double does not,
+        # so look at the modalities before concluding that the column is absent (tools.py:438-440)
+        in_all_mods = is_mudata(data) and all(hasattr(a.var, "columns") and use_var in a.var.columns for a in mdata.mod.values())
+        if not in_all_mods:
+            warn(f"There is no column {use_var} in the provided object")
+            use_var = None
     common_obs = None
     if is_mudata(data):
         common_obs = reduce(np.intersect1d, [np.asarray(v.obs_names) for v in mdata.mod.values()])
@@ -473,8 +625,8 @@ def mofa(
     lik = likelihoods
     if lik is not None:
         lik = [lik] * len(mdata.mod) if isinstance(lik, str) else list(lik)
-        if any(l != "gaussian" for l in lik):
-            raise NotImplementedError("only the gaussian likelihood is supported by the B200 path yet")
+        if len(lik) != len(mdata.mod) or any(l not in ("gaussian", "poisson", "bernoulli") for l in lik):
+            raise ValueError(f"likelihoods must be 'gaussian', 'poisson' or 'bernoulli' per modality, got {likelihoods!r}")
     if groups_label is not None and (not hasattr(mdata.obs, "columns") or groups_label not in mdata.obs.columns):
         raise KeyError(f"{groups_label} is not in observations names")     # reference prints and exits, tools.py:98-101
 
@@ -503,29 +655,29 @@ def mofa(
         masks.append(mask)
 
     if lik is None:
-        # The reference lets mofapy2 guess the likelihood per view (tools.py:272-280): all values in {0,1} ->
-        # bernoulli, all integers -> poisson, else gaussian.  Those two need dense N x D pseudo-data and are not
-        # implemented here: say so instead of silently fitting a different model.
-        for m, X in zip(mods, Xs):
-            vals = X.data if hasattr(X, "data") and not isinstance(X, np.ndarray) else np.asarray(X).ravel()
-            if isinstance(vals, torch.Tensor):
-                vals = vals[:: max(1, vals.numel() // 1_000_000)].cpu().numpy()
-            else:
-                vals = np.asarray(vals)[:: max(1, vals.size // 1_000_000)]
-            if vals.size and np.all(vals == np.round(vals)):
-                kind = "bernoulli" if np.all((vals == 0) | (vals == 1)) else "poisson"
-                warn(f"view '{m}' holds only integer values: the reference would pick the {kind} likelihood; "
-                     "muon_b200 fits the gaussian model (pass likelihoods='gaussian' to silence this)")
+        # The reference lets mofapy2 guess the likelihood per view (tools.py:272-280, mofapy2 guess_likelihoods):
+        # all values in {0,1} -> bernoulli, all integers -> poisson, else gaussian.
+        lik = [_guess_likelihood(X) for X in Xs]
+    for m, X, l in zip(mods, Xs, lik):
+        if l != "gaussian":
+            _check_dense_fits(m, X.shape, l, dev)
 
     if simple:
-        views = [_to_device_view(X) for X in Xs]
-        n_local, n_total, row0 = views[0].shape[0], views[0].n_total, views[0].row0
+        views = [_to_device_view(X) if l == "gaussian" else _to_dense_device(X, dev) for X, l in zip(Xs, lik)]
+        sparse_views = [v for v in views if isinstance(v, _device.DeviceCSR)]
+        n_local = views[0].shape[0]
+        if sparse_views:
+            n_total, row0 = sparse_views[0].n_total, sparse_views[0].row0
+        elif _dist.is_distributed():
+            raise NotImplementedError("cell-sharded mofa() needs at least one gaussian (DeviceCSR) view to carry the shard offsets")
+        else:
+            n_total, row0 = n_local, 0
         rs = np.random.RandomState(seed)
         Z0 = torch.from_numpy(rs.normal(size=(n_total, n_factors))[row0:row0 + n_local])
         res = run_mofa_device(views, n_factors, n_iterations, n_total, Z0, center=center_groups,
                               scale_views=scale_views, ard_weights=ard_weights, ard_factors=ard_factors,
                               spikeslab_weights=spikeslab_weights, convergence_mode=convergence_mode,
-                              verbose=verbose and not quiet)
+                              verbose=verbose and not quiet, likelihoods=lik)
         Z_full = res["Z"].cpu().numpy()
         group_names = ["group1"]
         variance = {m: res["variance"][i].cpu().numpy() for i, m in enumerate(mods)}
@@ -566,7 +718,10 @@ def mofa(
                 selg = (zpos >= lo) & (zpos < hi)
                 rows_z = zpos[selg]
                 Xg = X[order[selg]].astype(np.float32)
-                A = _device.DeviceCSR.from_scipy(sp.csr_matrix(Xg), dtype=np.float32)
+                if lik[mi] == "gaussian":
+                    A = _device.DeviceCSR.from_scipy(sp.csr_matrix(Xg), dtype=np.float32)
+                else:
+                    A = _to_dense_device(Xg, dev)
                 if len(rows_z) == hi - lo and np.array_equal(rows_z, np.arange(lo, hi)):
                     per_g.append((A, (lo, hi)))
                 else:
@@ -577,7 +732,7 @@ def mofa(
         rs = np.random.RandomState(seed)
         Z0 = torch.from_numpy(rs.normal(size=(N, n_factors)))
         model = MofaDevice(blocks, dims, group_ranges, [hi - lo for lo, hi in group_ranges], cls, n_factors, Z0,
-                           center_groups, scale_views, scale_groups, ard_weights, ard_factors, spikeslab_weights)
+                           center_groups, scale_views, scale_groups, ard_weights, ard_factors, spikeslab_weights, lik)
         res = _train(model, n_iterations, convergence_mode, True, True, verbose and not quiet)
         Zp = res["Z"].cpu().numpy()
         where = {c: i for i, c in enumerate(obs_all)}
@@ -603,7 +758,7 @@ def mofa(
     data.uns["mofa"] = {
         "params": {
             "data": {"groups_label": groups_label, "use_raw": use_raw, "use_layer": use_layer,
-                     "likelihoods": np.array(["gaussian"] * len(mods)), "features_subset": use_var,
+                     "likelihoods": np.array(lik), "features_subset": use_var,
                      "use_obs": use_obs, "scale_views": scale_views, "scale_groups": scale_groups,
                      "center_groups": center_groups, "use_float32": use_float32},
             "model": {"ard_factors": ard_factors, "ard_weights": ard_weights, "spikeslab_weights": spikeslab_weights,

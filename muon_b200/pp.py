@@ -13,9 +13,14 @@ from ._containers import is_mudata
 def _choose_representation(adata, use_rep=None, n_pcs=None):
     """scanpy.tools._utils._choose_representation for what muon passes (preproc.py:378)."""
     if use_rep is None or use_rep == "X":
-        if use_rep is None and "X_pca" in adata.obsm and adata.n_vars > 50:
-            X = adata.obsm["X_pca"]
-            return X[:, :n_pcs] if n_pcs else X
+        if use_rep is None and adata.n_vars > 50:
+            if "X_pca" in adata.obsm:
+                X = adata.obsm["X_pca"]
+                return X[:, :n_pcs] if n_pcs else X
+            # scanpy would compute a PCA here (n_vars > 50 and no X_pca); silently searching in the raw X instead
+            # would give a different graph, so ask for the representation explicitly
+            raise ValueError("use_rep is None, the modality has more than 50 variables and no .obsm['X_pca']: scanpy would "
+                             "compute a PCA at this point; run it first or set use_rep in the modality's neighbors call")
         return adata.X
     if use_rep in adata.obsm:
         X = adata.obsm[use_rep]
@@ -143,6 +148,13 @@ def neighbors(
     N, M = len(obs), len(modalities)
     if M > 4:
         raise NotImplementedError("more than 4 modalities")
+    # limits of the per-cell candidate tables (csrc/wnn.cu kWnnMaxCand) and of the exact kNN kernels, checked up
+    # front instead of failing data-dependently in the middle of the call
+    if M * n_multineighbors > 1536:
+        raise NotImplementedError(f"n_multineighbors * modalities = {M * n_multineighbors} > 1536 candidates per cell is not "
+                                  "supported by the B200 path yet")
+    if n_multineighbors + 1 > 320:
+        raise NotImplementedError("n_multineighbors > 319 is not supported by the B200 path yet (exact kNN kernels: k <= 320)")
 
     _device.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -193,8 +205,13 @@ def neighbors(
         cur, others = None, []
         for i2, m2 in enumerate(modalities):
             G2 = Gd[m2]
-            deg = (G2.indptr[1:] - G2.indptr[:-1]).to(torch.float32)
-            mean_graph = G2.with_data(torch.repeat_interleave(1.0 / deg, (G2.indptr[1:] - G2.indptr[:-1])))
+            # mean over the stored neighbours with a NON-ZERO distance (the reference takes graph.nonzero(),
+            # preproc.py:480-483, which skips explicitly stored zeros such as duplicate cells)
+            lens = G2.indptr[1:] - G2.indptr[:-1]
+            nz = (G2.data != 0).to(torch.float32)
+            rowid = torch.repeat_interleave(torch.arange(N, device=dev), lens)
+            deg = torch.zeros(N, dtype=torch.float32, device=dev).index_add_(0, rowid, nz)
+            mean_graph = G2.with_data(nz / deg.clamp_min(1.0)[rowid])
             r = _device.spmm(mean_graph, Xp, dynamic=False)[:, :d]       # mean of X over the cell's neighbours in m2
             dist = (X.to(torch.float64) - r.to(torch.float64)).norm(dim=1)
             theta = torch.exp(-torch.clamp(dist - nnd[m1], min=0) / (sig[m1] - nnd[m1]))

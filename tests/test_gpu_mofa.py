@@ -90,13 +90,20 @@ def test_api_semantics(cuda):
     lfs = out.varm["LFs"]
     assert lfs.shape == (200, 4)
     assert np.all(lfs[:120][np.arange(120) % 3 == 0] == 0) and np.any(lfs[:120][np.arange(120) % 3 != 0] != 0)
+    # the column only on the modalities (mudata would lift it into mdata.var): still honoured, no warning
+    md_b = SimpleMuData({"rna": a, "atac": b})
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        out_b = mu.tl.mofa(md_b, n_factors=4, n_iterations=20, copy=True)
+    np.testing.assert_allclose(out_b.varm["LFs"], lfs, rtol=1e-6, atol=1e-9)
     with pytest.raises(TypeError):
         mu.tl.mofa(np.ones((3, 3)))
     c = SimpleAnnData(views[1][:250])
     with pytest.raises(IndexError):
         mu.tl.mofa(SimpleMuData({"rna": a, "atac": c}), use_var=None)
-    with pytest.raises(NotImplementedError):
-        mu.tl.mofa(md, use_var=None, likelihoods="poisson")
+    with pytest.raises(ValueError):
+        mu.tl.mofa(md, use_var=None, likelihoods="negative_binomial")
 
 
 def test_groups_and_union_match_general_oracle(cuda):
@@ -173,3 +180,69 @@ def test_device_resident_views_and_layers(cuda):
     mu.tl.mofa(host, use_var=None, n_factors=4, n_iterations=15, likelihoods="gaussian")
     np.testing.assert_allclose(md.obsm["X_mofa"], host.obsm["X_mofa"], rtol=1e-4, atol=1e-5)
     assert md.uns["mofa"]["params"]["data"]["use_layer"] == "norm"
+
+
+def _count_views(N, seed):
+    rng = np.random.default_rng(seed)
+    Z = rng.normal(size=(N, 3))
+    W1 = rng.normal(size=(70, 3)) * (rng.random((70, 3)) < 0.5)
+    W2 = rng.normal(size=(45, 3)) * (rng.random((45, 3)) < 0.5)
+    W3 = rng.normal(size=(30, 3))
+    Yp = rng.poisson(np.log1p(np.exp(Z @ W1.T + 0.5))).astype(np.float64)
+    Yb = (rng.random((N, 45)) < 1 / (1 + np.exp(-(Z @ W2.T)))).astype(np.float64)
+    Yg = Z @ W3.T + rng.normal(size=(N, 30))
+    return Yp, Yb, Yg
+
+
+def test_poisson_bernoulli_views_match_oracle(cuda):
+    """Non-gaussian likelihoods (Seeger pseudo-data, dense views): guessed from the data exactly as mofapy2's
+    guess_likelihoods does when the reference passes likelihoods=None (tools.py:272-280); the fit equals the
+    float64 restatement from the same initial state."""
+    N, K, T = 400, 5, 25
+    Yp, Yb, Yg = _count_views(N, 0)
+    md = SimpleMuData({"counts": SimpleAnnData(sp.csr_matrix(Yp)), "binary": SimpleAnnData(Yb), "cont": SimpleAnnData(Yg)})
+    mu.tl.mofa(md, use_var=None, n_factors=K, n_iterations=T, convergence_mode="slow", seed=5)
+    assert list(md.uns["mofa"]["params"]["data"]["likelihoods"]) == ["poisson", "bernoulli", "gaussian"]
+    ref = mofa_ref_general([Yp, Yb, Yg], n_factors=K, n_iterations=T, convergence_mode="slow", seed=5,
+                           likelihoods=["poisson", "bernoulli", "gaussian"])
+    got_elbo = md.uns["mofa"]["_b200"]["elbo"]
+    assert len(got_elbo) == len(ref["elbo"])
+    np.testing.assert_allclose(got_elbo, ref["elbo"], rtol=2e-5)
+    act = np.sum([v.sum(0) for v in ref["variance"]], axis=0) > 2.0
+    assert act.sum() >= 2
+    Zg, Zr = md.obsm["X_mofa"], ref["Z"]
+    assert (np.abs(Zg - Zr).max(0) / np.abs(Zr).max(0))[act].max() < 5e-4
+    Wr = np.concatenate(ref["W"], axis=0)
+    assert (np.abs(md.varm["LFs"] - Wr).max(0) / np.abs(Wr).max(0))[act].max() < 5e-4
+    # explicit likelihoods override the guess; the planted structure is found either way
+    md2 = SimpleMuData({"counts": SimpleAnnData(sp.csr_matrix(Yp)), "cont": SimpleAnnData(Yg)})
+    mu.tl.mofa(md2, use_var=None, n_factors=K, n_iterations=T, likelihoods=["gaussian", "gaussian"], seed=5)
+    assert list(md2.uns["mofa"]["params"]["data"]["likelihoods"]) == ["gaussian", "gaussian"]
+    # groups + poisson through the general path
+    import pandas as pd
+    md3 = SimpleMuData({"counts": SimpleAnnData(sp.csr_matrix(Yp)), "cont": SimpleAnnData(Yg)})
+    grp = np.array(["a"] * 150 + ["b"] * 250)
+    md3.obs["grp"] = grp
+    mu.tl.mofa(md3, use_var=None, n_factors=K, n_iterations=15, convergence_mode="slow", groups_label="grp", seed=2)
+    ref3 = mofa_ref_general([Yp, Yg], groups=grp, n_factors=K, n_iterations=15, convergence_mode="slow", seed=2,
+                            likelihoods=["poisson", "gaussian"])
+    np.testing.assert_allclose(md3.uns["mofa"]["_b200"]["elbo"], ref3["elbo"], rtol=2e-5)
+
+
+def test_center_groups_false_uses_the_global_mean(cuda):
+    """center_groups=False still centres every feature (mean over all groups): with one group the flag changes
+    nothing, with two groups the fit equals the oracle's."""
+    views = _planted(300, [90, 60], 3, seed=21)
+    a = SimpleMuData({"rna": SimpleAnnData(views[0]), "atac": SimpleAnnData(views[1])})
+    b = SimpleMuData({"rna": SimpleAnnData(views[0]), "atac": SimpleAnnData(views[1])})
+    mu.tl.mofa(a, use_var=None, n_factors=4, n_iterations=12, convergence_mode="slow", center_groups=True)
+    mu.tl.mofa(b, use_var=None, n_factors=4, n_iterations=12, convergence_mode="slow", center_groups=False)
+    np.testing.assert_allclose(a.uns["mofa"]["_b200"]["elbo"], b.uns["mofa"]["_b200"]["elbo"], rtol=1e-9)
+    grp = np.array(["a"] * 100 + ["b"] * 200)
+    c = SimpleMuData({"rna": SimpleAnnData(views[0]), "atac": SimpleAnnData(views[1])})
+    c.obs["grp"] = grp
+    mu.tl.mofa(c, use_var=None, n_factors=4, n_iterations=12, convergence_mode="slow", center_groups=False,
+               groups_label="grp", seed=3)
+    ref = mofa_ref_general([v.toarray() for v in views], groups=grp, n_factors=4, n_iterations=12,
+                           convergence_mode="slow", center_groups=False, seed=3)
+    np.testing.assert_allclose(c.uns["mofa"]["_b200"]["elbo"], ref["elbo"], rtol=1e-5)
