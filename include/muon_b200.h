@@ -58,6 +58,20 @@ int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const fl
 int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const double* data,
                          int64_t n_rows, int32_t n_cols, double* row_sum, double* col_sum,
                          int32_t* status, uint32_t flags, mub_stream_t stream);
+/* pass 1, tiled variant for fp32 matrices whose rows hold SORTED column indices: a CTA owns mub_tfidf_tile_rows()
+ * rows and sweeps the columns tile by tile with the tile's column sums and entry counts in shared memory (two
+ * shared-memory atomics per non-zero, one global flush per tile) instead of one global atomic per non-zero.
+ * Same outputs and status bits as mub_tfidf_reduce_f32; status is mandatory (bit0 set = some row is not sorted:
+ * the sums are then invalid, use mub_tfidf_reduce_f32).  row_sum / indptr point at the first row of the call,
+ * row_base = its absolute row number (a multiple of the tile height).  Optional by-product: col_count
+ * [n_chunks x n_cols] int32 (zeroed by the caller, accumulated) = stored entries per (row chunk, column), row
+ * chunks given by chunk_bounds[n_chunks+1] (absolute rows, multiples of the tile height): the histogram
+ * mub_csr_transpose_count would otherwise compute in a pass of its own. */
+int mub_tfidf_reduce_tiled_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                               int32_t n_cols, float* row_sum, float* col_sum, int32_t* status, uint32_t flags,
+                               int32_t* col_count, const int64_t* chunk_bounds, int32_t n_chunks, int64_t row_base,
+                               mub_stream_t stream);
+int mub_tfidf_tile_rows(void);
 /* idf[j] = n_obs_total / col_sum[j], log1p if MUB_TFIDF_LOG_IDF (preproc.py:106-108) */
 int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags,
                       float* idf, mub_stream_t stream);

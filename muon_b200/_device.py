@@ -324,6 +324,33 @@ class DevicePairs:
 
 
 # ------------------------------------------------------------------------------------------
+N_CHUNKS = 16          # row chunks of the per-(chunk, column) entry counts; panel sets of 1/2/4/8/16 panels nest in them
+_TILE_ROWS = None
+
+
+def tile_rows() -> int:
+    global _TILE_ROWS
+    if _TILE_ROWS is None:
+        _TILE_ROWS = int(load().mub_tfidf_tile_rows())
+    return _TILE_ROWS
+
+
+def chunk_bounds(n: int, align: Optional[int] = None) -> list:
+    """Row boundaries of the N_CHUNKS row chunks of an n-row shard: i*n/16 rounded up to a multiple of the tiled
+    reduce kernel's block height (so that no CTA straddles a chunk), last = n.  The transposed row panels
+    (TransposedPanels) are unions of consecutive chunks, which lets them reuse the entry counts the TF-IDF
+    reduce pass produces."""
+    align = tile_rows() if align is None else align
+    b = [min(n, -(-round(i * n / N_CHUNKS) // align) * align) for i in range(N_CHUNKS)] + [n]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
+def tiled_reduce_enabled() -> bool:
+    return os.environ.get("MUON_B200_TFIDF_TILED", "1") != "0"
+
+
 def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=1e4,
               inplace_values=False, check_canonical=False, binarize=False) -> Optional[DeviceCSR]:
     """K1: two fused passes (reduce, apply).  Column sums are allreduced across cell shards
@@ -342,10 +369,27 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
     col_sum = torch.zeros(d, dtype=dt, device=dev)
     st = stream_ptr()
     status = torch.zeros(1, dtype=torch.int32, device=dev) if check_canonical else None
-    call(f"mub_tfidf_reduce_{sfx}", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(row_sum), ptr(col_sum),
-         ptr(status), flags, st)
-    if check_canonical and int(status[0]) != 0:
-        return None  # caller canonicalises (duplicates / explicit zeros / unsorted rows) and retries
+    counts = None
+    if sfx == "f32" and A.sorted_indices and tiled_reduce_enabled() and n > 0:
+        # shared-memory tiled pass: column sums + the transposition's entry counts, ~30x fewer global atomics
+        st_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        bounds = chunk_bounds(n)
+        counts = torch.zeros((N_CHUNKS, d), dtype=torch.int32, device=dev)
+        cb = torch.tensor(bounds, dtype=torch.int64, device=dev)
+        call("mub_tfidf_reduce_tiled_f32", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(row_sum), ptr(col_sum),
+             ptr(st_t), flags, ptr(counts), ptr(cb), N_CHUNKS, 0, st)
+        bad = int(st_t[0])
+        if check_canonical and bad != 0:
+            return None  # caller canonicalises (duplicates / explicit zeros / unsorted rows) and retries
+        if bad & 1:      # a row is not sorted after all: the tiled sums are invalid, take the order-agnostic kernel
+            A.sorted_indices = False
+            counts = None
+            col_sum.zero_()
+    if counts is None:
+        call(f"mub_tfidf_reduce_{sfx}", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(row_sum), ptr(col_sum),
+             ptr(status), flags, st)
+        if check_canonical and int(status[0]) != 0:
+            return None  # caller canonicalises (duplicates / explicit zeros / unsorted rows) and retries
     _dist.all_reduce_sum_(col_sum)
     idf = torch.empty(d, dtype=dt, device=dev)
     call(f"mub_tfidf_idf_{sfx}", ptr(col_sum), d, float(A.n_total), flags, ptr(idf), st)
@@ -354,11 +398,13 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
          ptr(idf), float(scale_factor), flags, st)
     res = A.with_data(out)
     res._aux = {"row_sum": row_sum, "col_sum": col_sum, "idf": idf}
+    if counts is not None:
+        res._aux["col_counts"] = (bounds, counts)
     return res
 
 
 def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None, k0: Optional[int] = None,
-                  k1: Optional[int] = None, pairs: bool = False):
+                  k1: Optional[int] = None, pairs: bool = False, col_count: Optional[torch.Tensor] = None):
     """Build the CSR of (A[row0:row1])^T on the device (count -> scan -> atomic-cursor fill).
     Row indices stored in the result are local to the panel (0 .. row1-row0).  ``k0``/``k1`` are the
     non-zero offsets of the row range if the caller already knows them (avoids a host sync)."""
@@ -375,7 +421,10 @@ def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None, k0: O
             k0, k1 = int(A.indptr[row0]), int(A.indptr[row1])
     nnz = k1 - k0
     t_count = torch.zeros(d + 1, dtype=torch.int64, device=dev)
-    call("mub_csr_transpose_count", ptr(A.indices) + 4 * k0, nnz, d, ptr(t_count), st)
+    if col_count is not None:      # entries per column of this row range, known from the TF-IDF reduce pass
+        t_count[1:] = col_count
+    else:
+        call("mub_csr_transpose_count", ptr(A.indices) + 4 * k0, nnz, d, ptr(t_count), st)
     t_indptr = torch.cumsum(t_count, 0)
     cursor = torch.empty(max(d, 1), dtype=torch.int64, device=dev)
     if pairs:
@@ -404,7 +453,21 @@ class TransposedPanels:
         n = A.shape[0]
         rows = max(1, self.L2_BUDGET // (4 * pad))
         n_panels = max(1, -(-n // rows))
-        bounds = [round(i * n / n_panels) for i in range(n_panels + 1)]
+        counts = None
+        if n_panels <= N_CHUNKS:
+            # 1, 2, 4, 8 or 16 panels, each a union of consecutive row chunks (see chunk_bounds): the entry counts
+            # per (chunk, column) left behind by the TF-IDF reduce pass then replace the counting pass
+            n_panels = 1 << (n_panels - 1).bit_length()
+            cb = chunk_bounds(n)
+            per = N_CHUNKS // n_panels
+            bounds = [cb[i * per] for i in range(n_panels)] + [n]
+            aux = getattr(A, "_aux", None) or {}
+            if "col_counts" in aux and list(aux["col_counts"][0]) == cb:
+                cc = aux["col_counts"][1]
+                counts = [cc[i * per:(i + 1) * per].sum(0, dtype=torch.int64) for i in range(n_panels)]
+        else:
+            bounds = [round(i * n / n_panels) for i in range(n_panels + 1)]
+        self.counts_reused = counts is not None
         self.shape = (A.shape[1], n)
         # non-zero offsets of the panel boundaries: one small D2H up front, no host syncs afterwards
         ks = A.indptr[torch.tensor(bounds, device=A.indptr.device)].tolist()
@@ -416,15 +479,17 @@ class TransposedPanels:
             side = torch.cuda.Stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True))
+                self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True,
+                                                                        col_count=counts[i] if counts else None))
                                for i in range(n_panels)]
                 self.ready = side.record_event()
             for _, _, T in self.panels:           # memory is consumed on the main stream later on
                 for t in (T.indptr, T.pairs):
                     t.record_stream(main)
         else:
-            self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True))
-                           for i in range(n_panels)]
+            self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True,
+                                                                    col_count=counts[i] if counts else None))
+                           for i in range(n_panels) if bounds[i + 1] > bounds[i]]
 
     def wait(self):
         if self.ready is not None:
@@ -545,15 +610,18 @@ def gram(Y: torch.Tensor, l: Optional[int] = None, weights: Optional[torch.Tenso
 _BLOCK_NNZ = int(os.environ.get("MUON_B200_BLOCK_NNZ", str(192 << 20)))
 
 
-def _row_blocks(indptr_host: np.ndarray, block_nnz: int):
-    """Cut rows into consecutive blocks of about ``block_nnz`` stored entries -> list of (r0, r1, k0, k1)."""
+def _row_blocks(indptr_host: np.ndarray, block_nnz: int, align: int = 1):
+    """Cut rows into consecutive blocks of about ``block_nnz`` stored entries -> list of (r0, r1, k0, k1); cuts are
+    multiples of ``align`` rows."""
     n = indptr_host.shape[0] - 1
     nnz = int(indptr_host[-1])
     if n == 0:
         return []
     nb = max(1, -(-nnz // max(block_nnz, 1)))
     targets = (np.arange(1, nb, dtype=np.float64) * (nnz / nb)).astype(np.int64)
-    cuts = np.unique(np.concatenate([[0], np.searchsorted(indptr_host, targets, side="left"), [n]]))
+    inner = np.searchsorted(indptr_host, targets, side="left")
+    inner = np.minimum(n, -(-inner // align) * align)
+    cuts = np.unique(np.concatenate([[0], inner, [n]]))
     return [(int(a), int(b), int(indptr_host[a]), int(indptr_host[b])) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
 
@@ -574,7 +642,8 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     indices_h = np.ascontiguousarray(X.indices)
     data_h = np.ascontiguousarray(X.data)
     nnz = int(indptr_h[-1]) if indptr_h.shape[0] else 0
-    blocks = _row_blocks(indptr_h, _BLOCK_NNZ)
+    tiled = tiled_reduce_enabled()
+    blocks = _row_blocks(indptr_h, _BLOCK_NNZ, tile_rows() if tiled else 1)
     st = stager()
     main = torch.cuda.current_stream()
     side = torch.cuda.Stream()
@@ -584,6 +653,9 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     row_sum = torch.empty(n, dtype=torch.float32, device=dev)
     col_sum = torch.zeros(d, dtype=torch.float32, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
+    bounds = chunk_bounds(n) if tiled else None
+    counts = torch.zeros((N_CHUNKS, d), dtype=torch.int32, device=dev) if tiled else None
+    cb = torch.tensor(bounds, dtype=torch.int64, device=dev) if tiled else None
     side.wait_stream(main)                      # allocations above are ordered on the main stream
     narrow = indices_h.dtype == np.int64
     assert narrow or indices_h.dtype == np.int32, indices_h.dtype
@@ -592,8 +664,12 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
         fp_idx.append(st.h2d(indices_h[k0:k1], indices[k0:k1], narrow=narrow, want_hash=True, stream=side))
         st.h2d(data_h[k0:k1], data[k0:k1], stream=side)
         main.wait_event(side.record_event())
-        call("mub_tfidf_reduce_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,
-             ptr(col_sum), ptr(status), flags, main.cuda_stream)
+        if tiled:      # host matrices must be canonical anyway (checked here): sorted rows, so the tiled pass applies
+            call("mub_tfidf_reduce_tiled_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,
+                 ptr(col_sum), ptr(status), flags, ptr(counts), ptr(cb), N_CHUNKS, r0, main.cuda_stream)
+        else:
+            call("mub_tfidf_reduce_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,
+                 ptr(col_sum), ptr(status), flags, main.cuda_stream)
     for t in (indices, data):
         t.record_stream(side)
     if int(status[0]) != 0:                     # duplicates / explicit zeros / unsorted rows (also syncs the upload)
@@ -623,6 +699,8 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     main.wait_stream(side)
     res = DeviceCSR(indptr, indices, data, (n, d), n_total=n_total)
     res._aux = {"row_sum": row_sum, "col_sum": col_sum, "idf": idf}
+    if tiled:
+        res._aux["col_counts"] = (bounds, counts)
     fps = {"blocks": [(k0, k1) for (_, _, k0, k1) in blocks], "indices": fp_idx, "data": fp_out,
            "indptr": host_pool().fingerprint(indptr_h.astype(np.int64, copy=False).view(np.uint32)) if n else 0}
     return res, out_h, fps

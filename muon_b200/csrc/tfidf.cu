@@ -83,6 +83,121 @@ tfidf_reduce_kernel(const int64_t* __restrict__ indptr, const int32_t* __restric
     if (status != nullptr && bad) atomicOr(status, bad);
 }
 
+// ---- tiled reduce (fp32, rows with sorted column indices) -----------------------------------------------
+// The kernel above issues one global RED per non-zero into the D-vector of column sums: 6e9 atomics at
+// BASELINE configs[1], and it is their rate (not HBM) that bounds it (31 ms, 18 % of DRAM bandwidth).  Here a CTA
+// owns a block of kTileRows rows and sweeps the column range tile by tile (kTileCols columns): the tile's
+// column sums AND entry counts live in shared memory, every non-zero costs two shared-memory atomics, and the
+// tile is flushed to global memory once per (row block, tile) -- ~30x fewer global atomics.  Rows are sorted, so
+// the entries of a row that fall in a tile are one contiguous segment; a per-row cursor in shared memory marks
+// where the next tile continues (no searching).  By-products, for free:
+//   * the entry count per (row chunk, column): exactly the histogram the CSR transposition needs
+//     (transpose.cu::transpose_count_kernel, one more pass of 6e9 global atomics otherwise),
+//   * the same canonical-form verdict: strictly increasing indices (bit0), explicit zeros (bit1).
+constexpr int kTileCols = 12288;   // 2 x 48 KB of shared memory per CTA -> 2 CTAs per SM
+constexpr int kTileRows = 512;
+constexpr int kTileThreads = 512;
+
+template <bool binarize>
+__global__ void __launch_bounds__(kTileThreads, 2)
+tfidf_reduce_tiled_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                          const float* __restrict__ data, int64_t n_rows, int32_t n_cols, float* __restrict__ row_sum,
+                          float* __restrict__ col_sum, int* __restrict__ status, int32_t* __restrict__ col_count,
+                          const int64_t* __restrict__ chunk_bounds, int32_t n_chunks, int64_t row_base) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sums = reinterpret_cast<float*>(smem_raw);
+    unsigned* cnts = reinterpret_cast<unsigned*>(smem_raw + sizeof(float) * kTileCols);
+    int* cur = reinterpret_cast<int*>(smem_raw + 2 * sizeof(float) * kTileCols);      // offset into the row
+    float* rsum = reinterpret_cast<float*>(cur + kTileRows);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kTileThreads / 32;
+    const int64_t r0 = (int64_t)blockIdx.x * kTileRows;
+    const int rows_here = (int)((n_rows - r0) < kTileRows ? (n_rows - r0) : kTileRows);
+    for (int r = threadIdx.x; r < kTileRows; r += kTileThreads) {
+        cur[r] = 0;
+        rsum[r] = 0.f;
+    }
+    // row chunk of this block (chunk bounds are multiples of kTileRows in absolute row numbers)
+    int chunk = 0;
+    if (col_count != nullptr) {
+        const int64_t abs_row = row_base + r0;
+        for (int c = 1; c < n_chunks; ++c) chunk += (abs_row >= chunk_bounds[c]) ? 1 : 0;
+    }
+    int bad = 0;
+    const int n_tiles = (n_cols + kTileCols - 1) / kTileCols;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int c_lo = t * kTileCols;
+        const int c_hi = (c_lo + kTileCols < n_cols) ? c_lo + kTileCols : n_cols;
+        for (int j = threadIdx.x; j < kTileCols; j += kTileThreads) {
+            sums[j] = 0.f;
+            cnts[j] = 0u;
+        }
+        __syncthreads();
+        for (int r = warp; r < rows_here; r += kWarps) {
+            const int64_t s0 = __ldg(indptr + r0 + r), e = __ldg(indptr + r0 + r + 1);
+            int64_t k = s0 + cur[r];
+            float acc = 0.f;
+            int prev_last = c_lo - 1;          // last column index seen in this tile's segment
+            for (;;) {
+                // three 32-wide segments in flight per lane
+                const int64_t k0 = k + lane, k1 = k0 + 32, k2 = k0 + 64;
+                const int c0 = k0 < e ? ld_stream(indices + k0) : 0x7fffffff;
+                const int c1 = k1 < e ? ld_stream(indices + k1) : 0x7fffffff;
+                const int c2 = k2 < e ? ld_stream(indices + k2) : 0x7fffffff;
+                float v0 = k0 < e ? ld_stream(data + k0) : 1.f;
+                float v1 = k1 < e ? ld_stream(data + k1) : 1.f;
+                float v2 = k2 < e ? ld_stream(data + k2) : 1.f;
+                int taken = 0;
+                bool stop = false;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int c = u == 0 ? c0 : (u == 1 ? c1 : c2);
+                    float v = u == 0 ? v0 : (u == 1 ? v1 : v2);
+                    const bool in = !stop && c < c_hi;             // warp-uniform `stop`, per-lane `c`
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    // entries of the tile form a prefix of the segment iff the row is sorted
+                    const int n_in = __popc(m);
+                    const bool prefix = (m == (n_in == 32 ? 0xffffffffu : ((1u << n_in) - 1u)));
+                    int p = __shfl_up_sync(0xffffffffu, c, 1);
+                    if (lane == 0) p = prev_last;
+                    if (in) {
+                        bad |= (c <= p) | (c < c_lo) | ((v == 0.f) << 1);
+                        if (binarize) v = v != 0.f ? 1.f : 0.f;
+                        if (c >= c_lo) {
+                            atomicAdd(&sums[c - c_lo], v);
+                            atomicAdd(&cnts[c - c_lo], 1u);
+                        }
+                        acc += v;
+                    }
+                    bad |= prefix ? 0 : 1;
+                    if (n_in > 0) prev_last = __shfl_sync(0xffffffffu, c, n_in - 1);
+                    taken += n_in;
+                    if (n_in < 32) stop = true;
+                }
+                k += taken;
+                if (stop || k >= e) break;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                cur[r] = (int)(k - s0);
+                rsum[r] += acc;
+                if (t == n_tiles - 1 && k != e) bad |= 1;     // left-over entries: index >= n_cols or unsorted
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < c_hi - c_lo; j += kTileThreads) {
+            const unsigned cn = cnts[j];
+            if (cn != 0u) {
+                atomicAdd(col_sum + c_lo + j, sums[j]);
+                if (col_count != nullptr) atomicAdd(col_count + (size_t)chunk * n_cols + c_lo + j, (int)cn);
+            }
+        }
+        __syncthreads();
+    }
+    for (int r = threadIdx.x; r < rows_here; r += kTileThreads) row_sum[r0 + r] = rsum[r];
+    if (status != nullptr && bad) atomicOr(status, bad);
+}
+
 template <typename T>
 __global__ void tfidf_idf_kernel(const T* __restrict__ col_sum, int32_t n_cols, T n_obs, uint32_t flags,
                                  T* __restrict__ idf) {
@@ -192,9 +307,39 @@ int tfidf_apply(const int64_t* indptr, const int32_t* indices, const T* data_in,
     return check_launch("tfidf_apply");
 }
 
+static size_t tiled_smem_bytes() { return 2 * sizeof(float) * kTileCols + 2 * sizeof(int) * kTileRows; }
+
 }  // namespace mub
 
 extern "C" {
+
+int mub_tfidf_reduce_tiled_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                               int32_t n_cols, float* row_sum, float* col_sum, int32_t* status, uint32_t flags,
+                               int32_t* col_count, const int64_t* chunk_bounds, int32_t n_chunks, int64_t row_base,
+                               mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_reduce_tiled: negative shape");
+    if (n_rows == 0) return 0;
+    MUB_REQUIRE(indptr && row_sum && col_sum && status, "tfidf_reduce_tiled: null pointer (status is mandatory: it reports rows "
+                "that are not sorted, for which the result is invalid)");
+    MUB_REQUIRE(col_count == nullptr || (chunk_bounds != nullptr && n_chunks >= 1), "tfidf_reduce_tiled: counts need chunk bounds");
+    MUB_REQUIRE((row_base % mub::kTileRows) == 0, "tfidf_reduce_tiled: row_base must be a multiple of %d", mub::kTileRows);
+    const size_t smem = mub::tiled_smem_bytes();
+    const int64_t grid = (n_rows + mub::kTileRows - 1) / mub::kTileRows;
+    MUB_REQUIRE(grid < (1ll << 31), "tfidf_reduce_tiled: too many rows");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (flags & MUB_TFIDF_BINARIZE) {
+        cudaFuncSetAttribute(mub::tfidf_reduce_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mub::tfidf_reduce_tiled_kernel<true><<<(int)grid, mub::kTileThreads, smem, s>>>(
+            indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, col_count, chunk_bounds, n_chunks, row_base);
+    } else {
+        cudaFuncSetAttribute(mub::tfidf_reduce_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        mub::tfidf_reduce_tiled_kernel<false><<<(int)grid, mub::kTileThreads, smem, s>>>(
+            indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, col_count, chunk_bounds, n_chunks, row_base);
+    }
+    return mub::check_launch("tfidf_reduce_tiled");
+}
+
+int mub_tfidf_tile_rows(void) { return mub::kTileRows; }
 
 int mub_tfidf_reduce_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
                          int32_t n_cols, float* row_sum, float* col_sum, int32_t* status, uint32_t flags,

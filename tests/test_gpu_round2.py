@@ -229,3 +229,66 @@ def test_host_path_pipeline_blocks_and_twin_validation(cuda, monkeypatch):
     ad2 = SimpleAnnData(C.copy())
     mu.atac.pp.tfidf(ad2)
     assert getattr(ad2.X, _device._RESIDENT_ATTR, None) is None
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_tiled_reduce_equals_atomic_reduce_and_counts_feed_the_transposition(cuda, monkeypatch):
+    """The shared-memory tiled reduce pass: row sums / column sums bit-identical to the one-atomic-per-non-zero
+    kernel (integer-valued counts: every order gives the same fp32 sum), entry counts per (row chunk, column)
+    equal to a bincount, panels built from those counts identical to panels built by the counting pass, and the
+    canonical-form verdict (unsorted row, explicit zero) unchanged."""
+    from muon_b200._lib import call, ptr, stream_ptr
+    C = generate_host(5000, 30000, 0.03, n_topics=8, seed=9)         # 3 column tiles, 10 row blocks
+    A = mu.DeviceCSR.from_scipy(C)
+    n, d = C.shape
+    monkeypatch.setenv("MUON_B200_TFIDF_TILED", "0")
+    ref = _device.tfidf_csr(A)
+    monkeypatch.setenv("MUON_B200_TFIDF_TILED", "1")
+    got = _device.tfidf_csr(A)
+    for key in ("row_sum", "col_sum", "idf"):
+        assert torch.equal(ref._aux[key], got._aux[key]), key
+    assert torch.equal(ref.data, got.data) and "col_counts" not in ref._aux
+    bounds, counts = got._aux["col_counts"]
+    assert bounds[0] == 0 and bounds[-1] == n and all(b % _device.tile_rows() == 0 for b in bounds[:-1])
+    for c in range(_device.N_CHUNKS):
+        lo, hi = int(C.indptr[bounds[c]]), int(C.indptr[bounds[c + 1]])
+        want = np.bincount(C.indices[lo:hi], minlength=d)
+        assert np.array_equal(counts[c].cpu().numpy(), want), c
+    # transposed panels from the reused counts == panels from the counting pass (same indptr; same entry SETS per row)
+    monkeypatch.setattr(_device.TransposedPanels, "L2_BUDGET", 1 << 18)       # 1024 cells per panel at pad 64 -> 8 panels
+    Tp = _device.TransposedPanels(got, 64)
+    Tq = _device.TransposedPanels(ref, 64)
+    assert Tp.counts_reused and not Tq.counts_reused and len(Tp.panels) == len(Tq.panels) >= 4
+    for (a0, a1, Ta), (b0, b1, Tb) in zip(Tp.panels, Tq.panels):
+        assert (a0, a1) == (b0, b1) and torch.equal(Ta.indptr, Tb.indptr)
+        Y = torch.randn((a1 - a0, 64), device=cuda)
+        np.testing.assert_allclose(_device.spmm(Ta, Y).cpu().numpy(), _device.spmm(Tb, Y).cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # binarize fused, float sums exact
+    gb = _device.tfidf_csr(A, binarize=True)
+    monkeypatch.setenv("MUON_B200_TFIDF_TILED", "0")
+    rb = _device.tfidf_csr(A, binarize=True)
+    assert torch.equal(gb.data, rb.data)
+    monkeypatch.setenv("MUON_B200_TFIDF_TILED", "1")
+    # an unsorted row: flagged (check_canonical) / silently handled by the order-agnostic kernel (device input)
+    Xu = C.copy()
+    a = Xu.indptr[777]
+    Xu.indices[a:a + 2] = C.indices[a:a + 2][::-1].copy()
+    Xu.data[a:a + 2] = C.data[a:a + 2][::-1].copy()
+    Au = mu.DeviceCSR.from_scipy(Xu)
+    assert _device.tfidf_csr(Au, check_canonical=True) is None
+    Au2 = mu.DeviceCSR.from_scipy(Xu)
+    out = _device.tfidf_csr(Au2)
+    assert not Au2.sorted_indices and torch.equal(out._aux["col_sum"], ref._aux["col_sum"])
+    # explicit zero: flagged under check_canonical, harmless otherwise
+    Xz = C.copy()
+    Xz.data[12345] = 0.0
+    assert _device.tfidf_csr(mu.DeviceCSR.from_scipy(Xz), check_canonical=True) is None
+    # index beyond n_cols is reported as non-canonical instead of corrupting shared memory
+    Xo = C.copy()
+    Xo.indices[Xo.indptr[100 + 1] - 1] = d + 5
+    st = torch.zeros(1, dtype=torch.int32, device=cuda)
+    Ao = mu.DeviceCSR.from_scipy(Xo)
+    rs, cs = torch.empty(n, device=cuda), torch.zeros(d, device=cuda)
+    call("mub_tfidf_reduce_tiled_f32", ptr(Ao.indptr), ptr(Ao.indices), ptr(Ao.data), n, d, ptr(rs), ptr(cs), ptr(st), 0,
+         None, None, 0, 0, stream_ptr())
+    assert int(st[0]) & 1
