@@ -784,7 +784,8 @@ def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
         return None
 
 
-def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Optional[str] = None):
+def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Optional[str] = None,
+           query_chunk: Optional[int] = None):
     """Exact k nearest neighbours in Euclidean distance (rows of Y closest to each row of X; Y defaults to X).
     Returns (indices int32 [n x k], distances float32 [n x k]), ascending, ties by lower index.  Groundwork for
     the WNN row (reference muon/_core/preproc.py:520-528).
@@ -796,6 +797,10 @@ def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Opti
     Y = X if Y is None else Y
     assert X.dtype == torch.float32 and Y.dtype == torch.float32 and X.is_contiguous() and Y.is_contiguous()
     assert X.shape[1] == Y.shape[1]
+    if query_chunk is not None and X.shape[0] > query_chunk:
+        # bounded workspace ("low_memory"): the queries in blocks, every block against all of Y -- same result
+        parts = [knn_l2(X[q0:q0 + query_chunk], k, Y, algo) for q0 in range(0, X.shape[0], query_chunk)]
+        return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
     nq, d = X.shape
     idx = torch.empty((nq, k), dtype=torch.int32, device=X.device)
     dist = torch.empty((nq, k), dtype=torch.float32, device=X.device)

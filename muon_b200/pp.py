@@ -97,8 +97,9 @@ def neighbors(
     ``uns[key]``, per-modality cell weights in ``obs["<mod>:mod_weight"]``.
 
     Differences, all deliberate: every nearest-neighbour search is **exact** (brute force on the GPU) where the
-    reference runs NN-descent, so ``low_memory`` and ``random_state`` have no effect; only the Euclidean metric and
-    dense representations are supported; all modalities must hold the same observations in the same order.
+    reference runs NN-descent, so ``random_state`` has no effect and ``low_memory`` only bounds the search workspace
+    (queries run in blocks of 131 072 cells); only the Euclidean metric is supported; sparse representations are
+    densified (same distances); all modalities must hold the same observations in the same order.
     """
     import scipy.sparse as sp
     import torch
@@ -133,7 +134,13 @@ def neighbors(
         params[mod] = nparams
         R = _choose_representation(mdata.mod[mod], use_rep, n_pcs)
         if sp.issparse(R):
-            raise NotImplementedError("sparse representations are not supported by the B200 path yet")
+            # sparse representation (reference: _jaccard_sparse_euclidean_metric / _sparse_csr_ptp, preproc.py:79-159,
+            # 425-447): Euclidean distances between sparse rows equal those between the densified rows, and the
+            # exact search needs the rows dense anyway -- densify if it fits, say so if it does not
+            if R.shape[0] * R.shape[1] * 4 > (8 << 30):
+                raise NotImplementedError(f"modality '{mod}': a sparse representation of shape {R.shape} does not fit the dense "
+                                          "exact search (8 GiB limit); reduce it first (PCA / LSI) and set use_rep")
+            R = R.toarray()
         reps[mod] = np.ascontiguousarray(np.asarray(R), dtype=np.float32)
         mod_reps[mod] = use_rep if use_rep is not None else -1
         mod_n_pcs[mod] = n_pcs if n_pcs is not None else -1
@@ -224,9 +231,12 @@ def neighbors(
     weights = torch.softmax(ratios, dim=1).contiguous()
 
     # ---- candidates: n_multineighbors exact neighbours per modality (preproc.py:509-567) ----------------------
+    # low_memory (reference: NN-descent's memory mode, default on above 50 000 cells, preproc.py:356-359,517): here it
+    # bounds the per-query workspace of the exact search by running the queries in blocks
+    lmem = low_memory if low_memory is not None else N > 50000
     cands = []
     for mod in modalities:
-        idx, _ = _device.knn_l2(Xd[mod], min(n_multineighbors + 1, N))
+        idx, _ = _device.knn_l2(Xd[mod], min(n_multineighbors + 1, N), query_chunk=131072 if lmem else None)
         cands.append(idx[:, 1:].contiguous())                            # drop the cell itself (preproc.py:531)
     n_cand = cands[0].shape[1]
 

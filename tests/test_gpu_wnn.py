@@ -67,6 +67,26 @@ def test_wnn_argument_errors(cuda):
     out = mu.pp.neighbors(md, n_multineighbors=30, key_added="wnn", add_weights_to_modalities=True, copy=True)
     assert "wnn_distances" in out.obsp and "wnn" in out.uns and "mod_weight" in out.mod["rna"].obs.columns
     assert "wnn_distances" not in md.obsp
+    with pytest.raises(NotImplementedError):                 # candidate-table limit, checked before any device work
+        mu.pp.neighbors(md, n_multineighbors=800)
+
+
+def test_wnn_sparse_representation_and_low_memory_blocks(cuda, monkeypatch):
+    """A sparse representation gives the same graph as its dense form (Euclidean distances between sparse rows,
+    reference preproc.py:425-447), and low_memory=True (queries in blocks) the same as low_memory=False."""
+    from muon_b200 import _device
+    z = load_golden("wnn_small.npz")
+    dense = _inputs(z)
+    mu.pp.neighbors(dense, n_multineighbors=40, low_memory=False)
+    sparse = _inputs(z)
+    sparse.mod["rna"].obsm["X_rep"] = sp.csr_matrix(sparse.mod["rna"].obsm["X_rep"])
+    orig = _device.knn_l2
+    monkeypatch.setattr(_device, "knn_l2", lambda X, k, Y=None, algo=None, query_chunk=None:
+                        orig(X, k, Y, algo, query_chunk=64 if query_chunk else None))     # 150 cells -> 3 blocks
+    mu.pp.neighbors(sparse, n_multineighbors=40, low_memory=True)
+    for key in ("distances", "connectivities"):
+        assert abs(sp.csr_matrix(dense.obsp[key]) - sp.csr_matrix(sparse.obsp[key])).max() < 1e-12
+    np.testing.assert_array_equal(dense.obs["rna:mod_weight"].to_numpy(), sparse.obs["rna:mod_weight"].to_numpy())
 
 
 def test_wnn_second_case_vs_numpy_restatement(cuda):
