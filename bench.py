@@ -321,6 +321,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    def note(tag, obj):
+        """progress on stderr (rank 0): a failing side leg must not cost the numbers of the legs before it"""
+        if rank == 0:
+            print(f"[bench] {tag}: {json.dumps(obj, default=str)[:1500]}", file=sys.stderr, flush=True)
+
     ctx = Ctx()
     ctx.world, ctx.rank, ctx.local = world, rank, local
     ctx.local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
@@ -356,6 +361,8 @@ def main():
         roofline["tfidf"] = {"achieved": 20.0 * nnz / (t * 1e-3) / 1e9, "unit": "GB/s", "ms": t,
                              "frac": 20.0 * nnz / (t * 1e-3) / 1e9 / hbm}
     phase_ms = {name: float(np.sum(v)) / args.steps for name, v in kern.items()}
+    note("main", {"value": value, "ms_per_step": ms_total / args.steps, "passes": info.passes,
+                  "lowp": getattr(info, "lowp_passes", 0), "history": info.history, "roofline": roofline, "phase_ms": phase_ms})
 
     breakdown = None
     if args.breakdown:
@@ -371,6 +378,7 @@ def main():
         ns = -(-args.cells // world)
         As = generate_device(ns, D, args.density, tables=tb, row0=rank * ns, n_total=ns * world)
         ms_s, kern_s, _, info_s, _ = timed_steps(ctx, lsi_step_fn(ctx, As, k, args.tol), args.steps, max(args.warmup, 1))
+        note("strong", {"ms_per_step": ms_s / args.steps})
         strong = {"cells_total": ns * world, "cells_per_gpu": ns, "ms_per_step": ms_s / args.steps,
                   "value": ns * world * args.steps / (ms_s / 1e3), "unit": "cells/s", "passes": info_s.passes,
                   "spmm_ms_per_step": float(np.sum([np.sum(v) for n_, v in kern_s.items() if "spmm" in n_])) / args.steps}
@@ -393,6 +401,7 @@ def main():
                "gpu_same_matrix_ms": ms_smp / 3, "gpu_same_matrix_passes": info_smp.passes,
                "same_matrix_speedup": (t_tfidf + t_lsi) / (ms_smp / 3e3)}
         del Xs
+        note("cpu_baseline", cpu)
 
     # ---- e2e: same public calls on HOST matrices -------------------------------------------------------------------
     e2e, X, Xt = None, None, None
@@ -418,6 +427,7 @@ def main():
         last = {}
 
         def step_host():
+            last.clear()                                       # drops the previous step's result (and its device twin)
             ad = mu.SimpleAnnData(X, obs=obs_df, var=var_df)   # tfidf rebinds ad.X; X itself is never modified
             t0 = time.perf_counter()
             mu.atac.pp.tfidf(ad)
@@ -449,6 +459,7 @@ def main():
                "cells_limited_by_host_ram": ne < ne_want,
                "path": "scipy csr on host -> mu.atac.pp.tfidf -> mu.atac.tl.lsi -> numpy slots (breakdown: host wall "
                        "seconds; h2d_s/d2h_s = time inside the staging engine, fingerprint_s = twin validation)"}
+        note("e2e", e2e)
         Xt = last.pop("X") if want_mofa else None          # host TF-IDF matrix: the ATAC view of the MOFA e2e leg
         last.clear()
         _device.release_all_resident()

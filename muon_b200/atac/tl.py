@@ -54,6 +54,11 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     P = _device.pad_width(min(n_comps + 8, 128) if n_comps + 8 <= 128 else n_comps)
     op = CsrOperator(A, P)
     U, s, V, info = truncated_svd(op, n_comps, P, tol=tol, seed=seed)
+    if not resident:
+        # the matrix on the device is a hidden copy (fresh upload or the twin left by tfidf): do not leave the
+        # 8 B/nnz transposed panels cached on it; a DeviceCSR the caller owns keeps them for the next call (mofa)
+        del op
+        A._tp = None
     if not info.converged:
         from warnings import warn
         warn(f"lsi: stopped after {info.passes} passes at relative residual {max(info.residuals):.1e} > tol={tol:g} "
