@@ -759,7 +759,9 @@ def release_all_resident() -> int:
     return n
 
 
-def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
+def resident_candidate(host_matrix):
+    """The device twin attached to a host matrix and its fingerprints, after the cheap checks (shape, nnz, dtypes);
+    None if there is none.  The twin may only be USED once ``resident_valid`` has confirmed it."""
     rec = getattr(host_matrix, _RESIDENT_ATTR, None)
     if rec is None or not resident_enabled():
         return None
@@ -769,19 +771,35 @@ def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
             return None
         if host_matrix.data.dtype != np.float32 or dev.data.dtype != torch.float32:
             return None
-        if host_matrix.indices.dtype not in (np.int32, np.int64):
+        if host_matrix.indices.dtype not in (np.int32, np.int64) or host_matrix.indptr.shape[0] != dev.shape[0] + 1:
             return None
+        return dev, fps
+    except Exception:
+        return None
+
+
+def resident_valid(host_matrix, fps) -> bool:
+    """Re-fingerprint every element of the host matrix (threaded read pass, no device work; the GIL is released, so
+    this can run on a helper thread under device work) and compare with what crossed the bus."""
+    try:
         pool = host_pool()
         indptr = np.ascontiguousarray(host_matrix.indptr).astype(np.int64, copy=False)
-        if indptr.shape[0] != dev.shape[0] + 1 or pool.fingerprint(indptr.view(np.uint32)) != fps["indptr"]:
-            return None
+        if pool.fingerprint(indptr.view(np.uint32)) != fps["indptr"]:
+            return False
         idx, dat = np.ascontiguousarray(host_matrix.indices), np.ascontiguousarray(host_matrix.data)
         for (k0, k1), hi, hd in zip(fps["blocks"], fps["indices"], fps["data"]):
             if pool.fingerprint(dat[k0:k1]) != hd or pool.fingerprint(idx[k0:k1]) != hi:
-                return None
-        return dev
+                return False
+        return True
     except Exception:
+        return False
+
+
+def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
+    cand = resident_candidate(host_matrix)
+    if cand is None:
         return None
+    return cand[0] if resident_valid(host_matrix, cand[1]) else None
 
 
 def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Optional[str] = None,
