@@ -73,6 +73,7 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
     if not resident:
         if check is not None and not check.result():          # the host matrix was edited after tfidf(): start over
             A._tp = None
+            _device.release_resident(Xs)
             del U, s, V
             A = _device.DeviceCSR.from_scipy(Xs, dtype=np.float32)
             U, s, V, info = solve(A)
