@@ -355,11 +355,15 @@ def main():
     roofline = spmm_roofline(ctx, kern, info, args.steps, nnz, n_local, D, k, clocks)
     pk, _ = peaks()
     hbm = float(pk.get("hbm_gbs", 6650.0))
-    tf_red, tf_app = kern.get("mub_tfidf_reduce_f32", []), kern.get("mub_tfidf_apply_f32", [])
+    tf_red = kern.get("mub_tfidf_reduce_f32", []) + kern.get("mub_tfidf_reduce_tiled_f32", [])
+    tf_app = kern.get("mub_tfidf_apply_f32", [])
     if tf_red and tf_app:
         t = float(np.mean(tf_red) + np.mean(tf_app))
         roofline["tfidf"] = {"achieved": 20.0 * nnz / (t * 1e-3) / 1e9, "unit": "GB/s", "ms": t,
-                             "frac": 20.0 * nnz / (t * 1e-3) / 1e9 / hbm}
+                             "ms_reduce": float(np.mean(tf_red)), "ms_apply": float(np.mean(tf_app)),
+                             "frac": 20.0 * nnz / (t * 1e-3) / 1e9 / hbm,
+                             "kernels": "tfidf_reduce_tiled_kernel (8 B/nnz) + tfidf_apply_kernel (12 B/nnz)"
+                             if "mub_tfidf_reduce_tiled_f32" in kern else "tfidf_reduce_kernel + tfidf_apply_kernel"}
     phase_ms = {name: float(np.sum(v)) / args.steps for name, v in kern.items()}
     note("main", {"value": value, "ms_per_step": ms_total / args.steps, "passes": info.passes,
                   "lowp": getattr(info, "lowp_passes", 0), "history": info.history, "roofline": roofline, "phase_ms": phase_ms})
@@ -463,6 +467,8 @@ def main():
         Xt = last.pop("X") if want_mofa else None          # host TF-IDF matrix: the ATAC view of the MOFA e2e leg
         last.clear()
         _device.release_all_resident()
+        if Xt is not None:
+            _device.release_resident(Xt)
         if not want_mofa:
             del X
             X = None

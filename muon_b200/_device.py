@@ -154,6 +154,53 @@ def device_fingerprint(t: torch.Tensor) -> int:
     return int(out[0]) & 0xFFFFFFFFFFFFFFFF
 
 
+def device_fingerprints(t: torch.Tensor, ranges) -> list:
+    """Fingerprints of the slices t[k0:k1] (positions counted from each slice's start), one host sync for all."""
+    assert t.is_contiguous() and t.element_size() == 4 and t.dim() == 1
+    out = torch.zeros(max(len(ranges), 1), dtype=torch.int64, device=t.device)
+    for i, (k0, k1) in enumerate(ranges):
+        call("mub_device_fingerprint", ptr(t) + 4 * k0, k1 - k0, ptr(out) + 8 * i, stream_ptr())
+    return [int(v) & 0xFFFFFFFFFFFFFFFF for v in out.tolist()][:len(ranges)]
+
+
+class _HostArena:
+    """Recycles large host result arrays.  Fresh anonymous memory is expensive here twice over -- the first touch
+    of every page while the download is written into it and the unmapping when the array dies (measured on the
+    benchmark host, a microVM: 12 GB/s into a fresh array against the staging rate into touched memory, seconds to
+    free 24 GB) -- so blocks are kept and handed out again once NOTHING references them any more (the arrays we
+    return are views whose ``base`` is the block, so a live result, or any view of it a caller holds, pins it).
+    At most $MUON_B200_HOST_CACHE_GB (default 64) are retained; ``trim()`` returns them to the OS."""
+
+    def __init__(self):
+        self.blocks = []
+        self.cap = int(float(os.environ.get("MUON_B200_HOST_CACHE_GB", "64")) * 2**30)
+
+    def empty(self, n: int, dtype) -> np.ndarray:
+        import sys
+        dt = np.dtype(dtype)
+        nbytes = int(n) * dt.itemsize
+        if nbytes < (64 << 20):
+            return np.empty(n, dtype=dt)
+        for b in self.blocks:
+            if nbytes <= b.nbytes <= 2 * nbytes and sys.getrefcount(b) == 3:      # list + loop variable + argument
+                return b[:nbytes].view(dt)
+        b = np.empty(nbytes, dtype=np.uint8)
+        if sum(x.nbytes for x in self.blocks) + nbytes <= self.cap:
+            self.blocks.append(b)
+        return b[:nbytes].view(dt)
+
+    def trim(self):
+        self.blocks = []
+
+
+_ARENA = _HostArena()
+
+
+def trim_host_cache():
+    """Give the retained host result buffers back to the OS."""
+    _ARENA.trim()
+
+
 _SMALL = 8 << 20
 
 
@@ -661,7 +708,7 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     assert narrow or indices_h.dtype == np.int32, indices_h.dtype
     fp_idx, fp_out = [], []
     for (r0, r1, k0, k1) in blocks:
-        fp_idx.append(st.h2d(indices_h[k0:k1], indices[k0:k1], narrow=narrow, want_hash=True, stream=side))
+        st.h2d(indices_h[k0:k1], indices[k0:k1], narrow=narrow, stream=side)
         st.h2d(data_h[k0:k1], data[k0:k1], stream=side)
         main.wait_event(side.record_event())
         if tiled:      # host matrices must be canonical anyway (checked here): sorted rows, so the tiled pass applies
@@ -682,7 +729,7 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
         n_total = int(_dist.all_reduce_sum_(t)[0])
     call("mub_tfidf_idf_f32", ptr(col_sum), d, float(n_total), flags, ptr(idf), main.cuda_stream)
     with _timed("alloc_out_s"):
-        out_h = np.empty(nnz, dtype=np.float32)
+        out_h = _ARENA.empty(nnz, np.float32)
 
     def apply(b):
         r0, r1, k0, k1 = blocks[b]
@@ -694,9 +741,14 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     for b, (r0, r1, k0, k1) in enumerate(blocks):
         ev_next = apply(b + 1) if b + 1 < len(blocks) else None
         side.wait_event(ev)
-        fp_out.append(st.d2h(data[k0:k1], out_h[k0:k1], want_hash=True, stream=side))
+        st.d2h(data[k0:k1], out_h[k0:k1], stream=side)
         ev = ev_next
     main.wait_stream(side)
+    # fingerprints of what crossed the bus, taken on the device copies (HBM-bound: ~10 ms per 24 GB) instead of
+    # inside the host-side staging loops
+    ranges = [(k0, k1) for (_, _, k0, k1) in blocks]
+    fp_idx = device_fingerprints(indices, ranges)
+    fp_out = device_fingerprints(data, ranges)
     res = DeviceCSR(indptr, indices, data, (n, d), n_total=n_total)
     res._aux = {"row_sum": row_sum, "col_sum": col_sum, "idf": idf}
     if tiled:
@@ -728,12 +780,13 @@ def remember_resident(host_matrix, dev: "DeviceCSR", fingerprints: dict):
         return
     try:
         setattr(host_matrix, _RESIDENT_ATTR, (dev, fingerprints))
-        import weakref
-        if _RESIDENT_REGISTRY is None:
-            _RESIDENT_REGISTRY = weakref.WeakSet()
-        _RESIDENT_REGISTRY.add(host_matrix)
     except Exception:
-        pass
+        return
+    import weakref
+    if _RESIDENT_REGISTRY is None:
+        _RESIDENT_REGISTRY = {}
+    key = id(host_matrix)                 # scipy matrices are not hashable: registry keyed by id, entries die with the matrix
+    _RESIDENT_REGISTRY[key] = weakref.ref(host_matrix, lambda _r, k=key: _RESIDENT_REGISTRY.pop(k, None))
 
 
 def release_resident(obj) -> bool:
@@ -754,12 +807,16 @@ def release_all_resident() -> int:
     """Drop every live device twin (e.g. before a memory-hungry mofa()/neighbors() call)."""
     n = 0
     if _RESIDENT_REGISTRY is not None:
-        for m in list(_RESIDENT_REGISTRY):
-            n += bool(release_resident(m))
+        for ref in list(_RESIDENT_REGISTRY.values()):
+            m = ref()
+            if m is not None:
+                n += bool(release_resident(m))
     return n
 
 
-def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
+def resident_candidate(host_matrix):
+    """The device twin attached to a host matrix and its fingerprints, after the cheap checks (shape, nnz, dtypes);
+    None if there is none.  The twin may only be USED once ``resident_valid`` has confirmed it."""
     rec = getattr(host_matrix, _RESIDENT_ATTR, None)
     if rec is None or not resident_enabled():
         return None
@@ -769,19 +826,35 @@ def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
             return None
         if host_matrix.data.dtype != np.float32 or dev.data.dtype != torch.float32:
             return None
-        if host_matrix.indices.dtype not in (np.int32, np.int64):
+        if host_matrix.indices.dtype not in (np.int32, np.int64) or host_matrix.indptr.shape[0] != dev.shape[0] + 1:
             return None
+        return dev, fps
+    except Exception:
+        return None
+
+
+def resident_valid(host_matrix, fps) -> bool:
+    """Re-fingerprint every element of the host matrix (threaded read pass, no device work; the GIL is released, so
+    this can run on a helper thread under device work) and compare with what crossed the bus."""
+    try:
         pool = host_pool()
         indptr = np.ascontiguousarray(host_matrix.indptr).astype(np.int64, copy=False)
-        if indptr.shape[0] != dev.shape[0] + 1 or pool.fingerprint(indptr.view(np.uint32)) != fps["indptr"]:
-            return None
+        if pool.fingerprint(indptr.view(np.uint32)) != fps["indptr"]:
+            return False
         idx, dat = np.ascontiguousarray(host_matrix.indices), np.ascontiguousarray(host_matrix.data)
         for (k0, k1), hi, hd in zip(fps["blocks"], fps["indices"], fps["data"]):
             if pool.fingerprint(dat[k0:k1]) != hd or pool.fingerprint(idx[k0:k1]) != hi:
-                return None
-        return dev
+                return False
+        return True
     except Exception:
+        return False
+
+
+def recall_resident(host_matrix) -> Optional["DeviceCSR"]:
+    cand = resident_candidate(host_matrix)
+    if cand is None:
         return None
+    return cand[0] if resident_valid(host_matrix, cand[1]) else None
 
 
 def knn_l2(X: torch.Tensor, k: int, Y: Optional[torch.Tensor] = None, algo: Optional[str] = None,

@@ -184,12 +184,12 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
     Returns (U [n_local x k] fp32, s [k] fp64, V [d x k] fp32, SvdInfo).  ``pad_to`` is the padded
     dense width the kernels run at (32/64/128); the Krylov block size is min(pad_to, d).
 
-    ``polish`` (default: $MUON_B200_LSI_POLISH, "1"): finish with scipy's Rayleigh-Ritz tail (one more pass over A).
+    ``polish`` (default: $MUON_B200_LSI_POLISH, "0"): finish with scipy's Rayleigh-Ritz tail (one more pass over A).
     ``False`` returns the Ritz triplets of the Krylov spaces themselves -- U_k from the stored left blocks -- and
-    saves that pass; on the CPU driver tests both are equally accurate (sigma 1e-7, vectors < 1e-6), the GPU parity
-    suite has only been run with the polish so far, hence the default.
+    saves that pass; both meet the same parity bar on the CPU driver tests and on the GPU suite (sigma 1e-7, vectors
+    < 1e-5 against float64 svds; tests/test_gpu_round2.py), so the cheaper one is the default since round 2.
 
-    ``lowp_tol`` (default: $MUON_B200_LSI_LOWP_TOL, "0" = off): if > ``tol`` and the operator supports it
+    ``lowp_tol`` (default: $MUON_B200_LSI_LOWP_TOL, "1e-3"; "0" = off): if > ``tol`` and the operator supports it
     (``op.lowp``), the iteration first runs with the dense operand of every product rounded to IEEE half -- half the
     bytes through the gather path that bounds the SpMM kernel -- until the wanted triplets reach ``lowp_tol``
     (rounding to half caps the attainable residual near 2e-4, so 1e-3 is the useful setting), then restarts in
@@ -198,9 +198,9 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
     cheaper.  ``SvdInfo.lowp_passes`` counts the half-precision passes.
     """
     if polish is None:
-        polish = os.environ.get("MUON_B200_LSI_POLISH", "1") != "0"
+        polish = os.environ.get("MUON_B200_LSI_POLISH", "0") != "0"
     if lowp_tol is None:
-        lowp_tol = float(os.environ.get("MUON_B200_LSI_LOWP_TOL", "0") or 0.0)
+        lowp_tol = float(os.environ.get("MUON_B200_LSI_LOWP_TOL", "1e-3") or 0.0)
     lowp = bool(getattr(op, "lowp", False)) and lowp_tol > tol
     d, dev, P = op.d, op.device, pad_to
     k = int(k)

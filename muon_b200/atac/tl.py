@@ -44,20 +44,41 @@ def lsi(data, scale_embeddings=True, n_comps=50, *, tol: float = 1e-5, seed: int
         import scipy.sparse as sp
         Xs = X if sp.issparse(X) else sp.csr_matrix(np.asarray(X))
         Xs = Xs.tocsr()  # row order inside a row is irrelevant to the SpMM kernels
-        A = _device.recall_resident(Xs)
-        if A is None:
+        # tfidf() may have left a device twin of this matrix.  It is used only if EVERY host element still equals
+        # what was downloaded; that check (a threaded read pass over the host arrays, GIL released) runs on a helper
+        # thread while the device already works on the twin, and a mismatch discards that work for a fresh upload.
+        cand = _device.resident_candidate(Xs)
+        check = None
+        if cand is not None:
+            from concurrent.futures import ThreadPoolExecutor
+            A = cand[0]
+            pool = ThreadPoolExecutor(1)
+            check = pool.submit(_device.resident_valid, Xs, cand[1])
+            pool.shutdown(wait=False)
+        else:
             A = _device.DeviceCSR.from_scipy(Xs, dtype=np.float32)
     n_total = A.n_total
     if n_comps >= min(n_total, A.shape[1]):  # svds' own requirement, scipy _svds.py:40-44
+        if not resident and check is not None:
+            check.result()
         raise ValueError(f"`k` must be an integer satisfying `0 < k < min(A.shape)` (k={n_comps})")
 
     P = _device.pad_width(min(n_comps + 8, 128) if n_comps + 8 <= 128 else n_comps)
-    op = CsrOperator(A, P)
-    U, s, V, info = truncated_svd(op, n_comps, P, tol=tol, seed=seed)
+
+    def solve(A):
+        op = CsrOperator(A, P)
+        return truncated_svd(op, n_comps, P, tol=tol, seed=seed)
+
+    U, s, V, info = solve(A)
     if not resident:
+        if check is not None and not check.result():          # the host matrix was edited after tfidf(): start over
+            A._tp = None
+            _device.release_resident(Xs)
+            del U, s, V
+            A = _device.DeviceCSR.from_scipy(Xs, dtype=np.float32)
+            U, s, V, info = solve(A)
         # the matrix on the device is a hidden copy (fresh upload or the twin left by tfidf): do not leave the
         # 8 B/nnz transposed panels cached on it; a DeviceCSR the caller owns keeps them for the next call (mofa)
-        del op
         A._tp = None
     if not info.converged:
         from warnings import warn

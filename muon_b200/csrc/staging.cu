@@ -24,54 +24,75 @@
 
 namespace mub {
 
-// ---- fingerprint: H = sum_i (e_i + C1) * (i * C2 + C3)  mod 2^64 over 32-bit elements e_i.  Every
-// term carries its position, so partial sums over disjoint ranges just add up (thread- and
-// chunk-order independent) while any permutation or single-element edit changes the value.
-constexpr uint64_t kH1 = 0x9E3779B97F4A7C15ull, kH2 = 0xD6E8FEB86659FD93ull, kH3 = 0xA0761D6478BD642Full;
+// ---- fingerprint of a stream of 32-bit elements e_i, i = 0..n-1:
+//        H = sum_i  u64(e_i ^ a_i) * u64(b_i)   mod 2^64,     a_i = u32(i*K1 + hi(i)*K3 + C1),  b_i = u32(i*K2 + hi(i)*K4 + C2) | 1
+// Every term carries its position, so partial sums over disjoint ranges just add up (thread- and chunk-order
+// independent), while any single-element edit (b_i is odd: x -> x*b_i is injective on 32-bit x) or permutation
+// changes the value.  32 x 32 -> 64-bit products only: the host loop vectorises (vpmuludq), the device kernel is
+// trivially HBM-bound.  hi(i) = i >> 32 keeps positions beyond 2^32 distinct.
+constexpr uint32_t kK1 = 0x9E3779B1u, kK2 = 0x85EBCA6Bu, kK3 = 0xC2B2AE35u, kK4 = 0x27D4EB2Fu, kC1 = 0x7F4A7C15u,
+                   kC2 = 0x165667B1u;
 
 __host__ __device__ inline uint64_t hash_term(uint32_t e, uint64_t i) {
-    return ((uint64_t)e + kH1) * (i * kH2 + kH3);
+    const uint32_t lo = (uint32_t)i, hi = (uint32_t)(i >> 32);
+    const uint32_t a = lo * kK1 + hi * kK3 + kC1;
+    const uint32_t b = (lo * kK2 + hi * kK4 + kC2) | 1u;
+    return (uint64_t)(e ^ a) * (uint64_t)b;
 }
 
-// copy `n` elements starting at logical position `pos0`; returns their fingerprint contribution
-static uint64_t copy_hash_u32(uint32_t* dst, const uint32_t* src, size_t n, uint64_t pos0, bool want_hash) {
-    if (!want_hash) {
-        memcpy(dst, src, n * 4);
-        return 0;
-    }
+// [pos0, pos0 + n) must not cross a multiple of 2^32 (callers split there), so hi(i) is a loop constant
+#if defined(__GNUC__) && !defined(__CUDA_ARCH__)
+#define MUB_SIMD_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define MUB_SIMD_CLONES
+#endif
+
+MUB_SIMD_CLONES static uint64_t hash_run_u32(const uint32_t* src, size_t n, uint64_t pos0) {
+    const uint32_t hi = (uint32_t)(pos0 >> 32), lo0 = (uint32_t)pos0;
+    const uint32_t abase = hi * kK3 + kC1, bbase = hi * kK4 + kC2;
     uint64_t h = 0;
-    for (size_t i = 0; i < n; ++i) {
-        const uint32_t e = src[i];
-        dst[i] = e;
-        h += hash_term(e, pos0 + i);
+    for (size_t j = 0; j < n; ++j) {
+        const uint32_t lo = lo0 + (uint32_t)j;
+        const uint32_t a = lo * kK1 + abase, b = (lo * kK2 + bbase) | 1u;
+        h += (uint64_t)(src[j] ^ a) * (uint64_t)b;
     }
     return h;
 }
 
-static uint64_t narrow_hash_i64(int32_t* dst, const int64_t* src, size_t n, uint64_t pos0, bool want_hash,
-                                int* overflow) {
+MUB_SIMD_CLONES static uint64_t hash_run_i64(const int64_t* src, size_t n, uint64_t pos0) {
+    const uint32_t hi = (uint32_t)(pos0 >> 32), lo0 = (uint32_t)pos0;
+    const uint32_t abase = hi * kK3 + kC1, bbase = hi * kK4 + kC2;
     uint64_t h = 0;
-    int bad = 0;
-    for (size_t i = 0; i < n; ++i) {
-        const int64_t v = src[i];
-        bad |= (v != (int64_t)(int32_t)v);
-        dst[i] = (int32_t)v;
-        if (want_hash) h += hash_term((uint32_t)(int32_t)v, pos0 + i);
+    for (size_t j = 0; j < n; ++j) {
+        const uint32_t lo = lo0 + (uint32_t)j;
+        const uint32_t a = lo * kK1 + abase, b = (lo * kK2 + bbase) | 1u;
+        h += (uint64_t)((uint32_t)src[j] ^ a) * (uint64_t)b;
     }
-    if (bad) *overflow = 1;
     return h;
 }
 
 static uint64_t hash_only(const void* src, size_t n, int elem_bytes, uint64_t pos0) {
     uint64_t h = 0;
-    if (elem_bytes == 8) {
-        const int64_t* s = (const int64_t*)src;
-        for (size_t i = 0; i < n; ++i) h += hash_term((uint32_t)(int32_t)s[i], pos0 + i);
-    } else {
-        const uint32_t* s = (const uint32_t*)src;
-        for (size_t i = 0; i < n; ++i) h += hash_term(s[i], pos0 + i);
+    size_t done = 0;
+    while (done < n) {                                    // split at multiples of 2^32
+        const uint64_t p = pos0 + done;
+        const uint64_t room = ((p >> 32) + 1) * (1ull << 32) - p;
+        const size_t m = (n - done) < room ? (n - done) : (size_t)room;
+        h += elem_bytes == 8 ? hash_run_i64((const int64_t*)src + done, m, p) : hash_run_u32((const uint32_t*)src + done, m, p);
+        done += m;
     }
     return h;
+}
+
+// int64 -> int32 narrowing of one run (vectorises); returns non-zero if a value does not fit
+MUB_SIMD_CLONES static int narrow_i64(int32_t* dst, const int64_t* src, size_t n) {
+    int64_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const int64_t v = src[i];
+        dst[i] = (int32_t)v;
+        bad |= (v ^ (int64_t)(int32_t)v);
+    }
+    return bad != 0;
 }
 
 // ---- a small persistent worker pool: run(fn, parts) executes fn(part) for part in [0, parts) ------
@@ -249,14 +270,13 @@ int mub_stager_h2d(void* handle, const void* src_h, void* dst, size_t n_elems, i
             if (i0 >= cnt) { partial[p] = 0; return; }
             const size_t m = cnt - i0 < per ? cnt - i0 : per;
             if (narrow) {
-                partial[p] = narrow_hash_i64((int32_t*)stage + i0, (const int64_t*)src + i0, m, off + i0, hash_h != nullptr,
-                                             &overflow);
-            } else if (src_elem_bytes == 4) {
-                partial[p] = copy_hash_u32((uint32_t*)stage + i0, (const uint32_t*)src + i0, m, off + i0, hash_h != nullptr);
+                if (narrow_i64((int32_t*)stage + i0, (const int64_t*)src + i0, m)) overflow = 1;
             } else {
                 memcpy(stage + i0 * src_elem_bytes, src + i0 * src_elem_bytes, m * src_elem_bytes);
-                partial[p] = 0;
             }
+            // fingerprints are normally taken on the DEVICE copy (mub_device_fingerprint, ~10 ms for 24 GB); the
+            // host-side variant costs a second pass over the chunk while it is hot in cache
+            partial[p] = hash_h ? hash_only(narrow ? (const void*)((int32_t*)stage + i0) : (const void*)(stage + i0 * 4), m, 4, off + i0) : 0;
         };
         s->pool->run(fn, parts);
         for (int p = 0; p < parts; ++p) hash += partial[p];
@@ -312,12 +332,8 @@ int mub_stager_d2h(void* handle, const void* src, void* dst_h, size_t n_bytes, u
             const size_t i0 = (size_t)p * per;
             if (i0 >= cnt) { partial[p] = 0; return; }
             const size_t m = cnt - i0 < per ? cnt - i0 : per;
-            if (hash_h)
-                partial[p] = copy_hash_u32((uint32_t*)(dst + i0), (const uint32_t*)(stage + i0), m / 4, (off + i0) / 4, true);
-            else {
-                memcpy(dst + i0, stage + i0, m);
-                partial[p] = 0;
-            }
+            memcpy(dst + i0, stage + i0, m);
+            partial[p] = hash_h ? hash_only(stage + i0, m / 4, 4, (off + i0) / 4) : 0;
         };
         s->pool->run(fn, parts);
         for (int p = 0; p < parts; ++p) hash += partial[p];

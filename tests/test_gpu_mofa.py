@@ -238,7 +238,8 @@ def test_center_groups_false_uses_the_global_mean(cuda):
     b = SimpleMuData({"rna": SimpleAnnData(views[0]), "atac": SimpleAnnData(views[1])})
     mu.tl.mofa(a, use_var=None, n_factors=4, n_iterations=12, convergence_mode="slow", center_groups=True)
     mu.tl.mofa(b, use_var=None, n_factors=4, n_iterations=12, convergence_mode="slow", center_groups=False)
-    np.testing.assert_allclose(a.uns["mofa"]["_b200"]["elbo"], b.uns["mofa"]["_b200"]["elbo"], rtol=1e-9)
+    # (the transposed panels are filled in atomic-claim order: fp32 sums differ run to run in the last bits)
+    np.testing.assert_allclose(a.uns["mofa"]["_b200"]["elbo"], b.uns["mofa"]["_b200"]["elbo"], rtol=1e-5)
     grp = np.array(["a"] * 100 + ["b"] * 200)
     c = SimpleMuData({"rna": SimpleAnnData(views[0]), "atac": SimpleAnnData(views[1])})
     c.obs["grp"] = grp

@@ -28,6 +28,8 @@ def test_stager_roundtrip_narrowing_and_fingerprints(cuda):
     torch.cuda.synchronize()
     assert np.array_equal(d.cpu().numpy(), a.astype(np.int32))
     assert h == st.fingerprint(a) == st.fingerprint(a.astype(np.int32)) == _device.device_fingerprint(d)
+    cuts = [(0, 1000), (1000, n // 2), (n // 2, n)]
+    assert _device.device_fingerprints(d, cuts) == [st.fingerprint(a[k0:k1]) for k0, k1 in cuts]
     back = np.empty(n, dtype=np.int32)
     h2 = st.d2h(d, back, want_hash=True)
     assert h2 == h and np.array_equal(back, a.astype(np.int32))
@@ -91,7 +93,7 @@ def test_spmm_half_operand(cuda, P):
     assert np.abs(W - refT).max() <= 2e-6 * np.abs(refT).max()
 
 
-@pytest.mark.parametrize("polish,lowp_tol", [(False, 0.0), (True, 1e-3), (False, 1e-3)])
+@pytest.mark.parametrize("polish,lowp_tol", [(True, 0.0), (False, 0.0), (True, 1e-3), (False, 1e-3)])
 @pytest.mark.parametrize("shape,k", [((3000, 2000), 15), ((2500, 1500), 60)])
 def test_lsi_cheaper_schedules_vs_svds_float64_truth(cuda, monkeypatch, shape, k, polish, lowp_tol):
     """The driver's cheaper schedules meet the same parity bar as the default: no final Rayleigh-Ritz pass
@@ -223,8 +225,20 @@ def test_host_path_pipeline_blocks_and_twin_validation(cuda, monkeypatch):
     out = mu.atac.pp.tfidf(SimpleAnnData(C), inplace=False)
     assert out.indices is not C.indices and out.indptr is not C.indptr
     np.testing.assert_array_equal(out.data, ref.data)
-    # twins can be switched off and released
+    # twins can be switched off and released (also all at once: the registry must see unhashable scipy matrices)
     assert _device.release_resident(ad) and _device.recall_resident(ad.X) is None
+    ad3 = SimpleAnnData(C.copy())
+    mu.atac.pp.tfidf(ad3)
+    assert _device.recall_resident(ad3.X) is not None and _device.release_all_resident() >= 1
+    assert _device.recall_resident(ad3.X) is None
+    # host result buffers are recycled once nothing references them, never while a view is alive
+    big = _device._ARENA.empty(40_000_000, np.float32)
+    keep = big[5:10]
+    addr = big.ctypes.data
+    del big
+    assert _device._ARENA.empty(40_000_000, np.float32).ctypes.data != addr       # `keep` still pins the block
+    del keep
+    assert _device._ARENA.empty(40_000_000, np.float32).ctypes.data == addr
     monkeypatch.setenv("MUON_B200_RESIDENT", "0")
     ad2 = SimpleAnnData(C.copy())
     mu.atac.pp.tfidf(ad2)
@@ -249,7 +263,7 @@ def test_tiled_reduce_equals_atomic_reduce_and_counts_feed_the_transposition(cud
         assert torch.equal(ref._aux[key], got._aux[key]), key
     assert torch.equal(ref.data, got.data) and "col_counts" not in ref._aux
     bounds, counts = got._aux["col_counts"]
-    assert bounds[0] == 0 and bounds[-1] == n and all(b % _device.tile_rows() == 0 for b in bounds[:-1])
+    assert bounds[0] == 0 and bounds[-1] == n and all(b % _device.tile_rows() == 0 or b == n for b in bounds)
     for c in range(_device.N_CHUNKS):
         lo, hi = int(C.indptr[bounds[c]]), int(C.indptr[bounds[c + 1]])
         want = np.bincount(C.indices[lo:hi], minlength=d)

@@ -85,11 +85,11 @@ def test_block_lanczos_matches_svds(k, P):
     ref = lsi_ref(X, k + 1, dtype=np.float64)
     s_next = ref["svalues"][k]
     ref = {"svalues": ref["svalues"][:k], "U": ref["U"][:, :k], "LSI": ref["LSI"][:, :k]}
-    U, s, V, info = truncated_svd(ScipyOperator(X), k, P, tol=1e-5)
+    U, s, V, info = truncated_svd(ScipyOperator(X), k, P, tol=1e-5, polish=True)
     assert info.converged
     out = compare_lsi({"svalues": s.numpy(), "U": U.numpy(), "LSI": V.numpy()}, ref, rtol=1e-4, s_next=s_next)
     assert out["sigma_rel"] < 1e-5
-    # without the final Rayleigh-Ritz pass (opt-in): same accuracy from the Krylov spaces alone, one pass fewer
+    # without the final Rayleigh-Ritz pass (the default): same accuracy from the Krylov spaces alone, one pass fewer
     U2, s2, V2, info2 = truncated_svd(ScipyOperator(X), k, P, tol=1e-5, polish=False)
     assert info2.passes == info.passes - 1 and U2.shape == U.shape
     out2 = compare_lsi({"svalues": s2.numpy(), "U": U2.numpy(), "LSI": V2.numpy()}, ref, rtol=1e-4, s_next=s_next)
@@ -249,10 +249,10 @@ def test_host_fingerprint_pool_only():
     a = rng.integers(0, 2**31 - 1, 3_000_001, dtype=np.int64)
     h = [_device.Stager(pool_only=True, threads=t).fingerprint(a) for t in (1, 3, 8)]
     assert h[0] == h[1] == h[2] == _device.Stager(pool_only=True, threads=2).fingerprint(a.astype(np.int32))
-    # the definition: sum_i (e_i + C1) * (i*C2 + C3) mod 2^64
-    C1, C2, C3, M = 0x9E3779B97F4A7C15, 0xD6E8FEB86659FD93, 0xA0761D6478BD642F, (1 << 64) - 1
+    # the definition: sum_i u64(e_i ^ a_i) * u64(b_i) mod 2^64, a_i = u32(i*K1 + C1), b_i = u32(i*K2 + C2) | 1  (i < 2^32)
+    K1, K2, C1, C2, M32, M = 0x9E3779B1, 0x85EBCA6B, 0x7F4A7C15, 0x165667B1, (1 << 32) - 1, (1 << 64) - 1
     small = [5, 0, 2**31 - 2, 77]
-    want = sum(((e + C1) & M) * ((i * C2 + C3) & M) for i, e in enumerate(small)) & M
+    want = sum((e ^ ((i * K1 + C1) & M32)) * (((i * K2 + C2) & M32) | 1) for i, e in enumerate(small)) & M
     assert _device.Stager(pool_only=True, threads=2).fingerprint(np.array(small, dtype=np.int32)) == want
     b = a.copy()
     b[[1, 2_999_999]] = b[[2_999_999, 1]]
