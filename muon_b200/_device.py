@@ -54,7 +54,9 @@ class _timed:
 
 def copy_threads() -> int:
     """Host threads that fill / drain the pinned staging ring: $MUON_B200_COPY_THREADS, else half the cores this
-    process may use divided by the ranks sharing the host (torchrun's LOCAL_WORLD_SIZE), clamped to [4, 48]."""
+    process may use divided by the ranks sharing the host (torchrun's LOCAL_WORLD_SIZE), clamped to [4, 16]:
+    on the benchmark host 16 threads reach 44-49 GB/s of the 55 GB/s the DMA engine delivers from pinned memory,
+    more threads are slower (profiles/staging_probe_r2.json: 48 threads 21-38 GB/s, 96 threads 10-19 GB/s)."""
     env = os.environ.get("MUON_B200_COPY_THREADS")
     if env:
         return max(1, int(env))
@@ -63,7 +65,7 @@ def copy_threads() -> int:
     except Exception:
         cores = os.cpu_count() or 8
     local = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    return int(min(48, max(4, cores // (2 * local))))
+    return int(min(16, max(4, cores // (2 * local))))
 
 
 class Stager:

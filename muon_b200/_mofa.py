@@ -11,11 +11,13 @@ sharded across ranks; ``P``, the K x K Gram and K-vectors are sum-allreduced (SU
 The update equations and their order are those of oracle/mofa_ref.py (see its header for the
 parity status against mofapy2).
 
-Supported: gaussian likelihood, one group, no missing values, ``use_var`` feature subsets,
-``scale_views``, ``center_groups``, ARD on weights / factors, spike-and-slab weights, convergence
-modes, ``copy``.  Not yet: ``groups_label``, ``use_obs`` (ragged observations), non-gaussian
-likelihoods, SVI, MEFISTO smoothing, HDF5 ``outfile`` (h5py is not available) -- these raise
-``NotImplementedError`` instead of silently doing something else.
+Supported: gaussian views kept sparse (implicit centring), poisson / bernoulli views as dense Seeger pseudo-data
+(guessed from the data like mofapy2 does when ``likelihoods=None``), ``groups_label``, ``use_obs`` union /
+intersection (cells missing from whole views), ``use_var`` feature subsets, ``use_layer``, ``scale_views``,
+``scale_groups``, ``center_groups``, ARD on weights / factors, spike-and-slab weights, convergence modes, ``copy``;
+the one-group case also cell-sharded over several GPUs.  Not supported (``NotImplementedError``, never a silent
+substitute): ``spikeslab_factors``, ``use_raw``, SVI, MEFISTO smoothing; ``outfile`` (HDF5) is ignored (h5py is not
+available); ``n_factors`` > 64.
 """
 from __future__ import annotations
 

@@ -16,6 +16,42 @@ planted 5 factors, 10 fitted, per-factor R^2 > 0.1 for the first five and <= 0.1
 factors sorted by variance explained) -- see tests/test_oracle_mofa.py.  The CUDA path is then
 checked against THIS restatement from an identical initial state.
 
+What this restatement assumes about mofapy2, item by item (everything marked [recalled] is from memory of the
+mofapy2 sources -- build_model/init_model.py, core/nodes/*.py, run/entry_point.py -- and of the papers'
+supplementary methods; none of it can be checked in this container, which is why parity is called UNPINNED):
+
+  item                     | value used here                                   | source
+  -------------------------+---------------------------------------------------+------------------------------------------
+  update order / iteration | Y(pseudo-data) -> W -> Z -> AlphaW -> AlphaZ ->    | MOFA 2018 Suppl. Methods "Inference: update
+                           | ThetaW -> Tau, then ELBO                           | schedule"; mofapy2 entry_point default
+                           |                                                   | schedule [recalled; mofapy2 may update Z
+                           |                                                   | before W -- both are valid CAVI orders and
+                           |                                                   | reach the same fixed points]
+  init Z                   | N(0,1) draws from np.random.RandomState(seed)      | init_model.initZ(qmean="random") [recalled];
+                           |                                                   | RNG stream not reproducible -> golden Z of
+                           |                                                   | tests/test_muon_tools.py:139-147 unreachable
+  init W                   | E[w] = 0, q(s=1) = 1                              | initW defaults [recalled]
+  init alpha, tau          | E = 1 (qa = qb = 1)                               | initAlpha*/initTau(qa=1, qb=1) [recalled]
+  prior alpha (W and Z)    | Gamma(a0 = 1e-3, b0 = 1e-3)                        | initAlphaW/Z(pa=1e-3, pb=1e-3) [recalled;
+                           |                                                   | MOFA v1 used 1e-14]
+  prior tau                | Gamma(1e-3, 1e-3)                                 | initTau(pa=1e-3, pb=1e-3) [recalled]
+  prior theta              | Beta(1, 1); initial E ln theta ~ 0 (q(s=1)=1)      | initThetaW(pa=1, pb=1) [recalled]
+  spike-and-slab W         | q(what, s): slab N(m, 1/a), spike N(0, 1/E[alpha]) | MOFA 2018 Suppl. "Spike-and-slab prior on the
+                           | logit q(s=1) = E ln(theta/(1-theta)) + ln E[alpha]/2| weights" (reparametrised w = s * what)
+                           |                 - ln(a)/2 + b^2/(2a)               |
+  Z prior                  | N(0, 1/alphaZ_gk) per group (ard_factors) else N(0,1)| MOFA+ 2020 Methods "ARD prior on the factors"
+  centring / scaling       | gaussian views: per-group means (center_groups) or | mofapy2 process_data [recalled]
+                           | the global mean; scale_views: global std; scale_   |
+                           | groups: per-group std; non-gaussian: neither       |
+  non-gaussian views       | Seeger pseudo-data, fixed kappa (see               | Seeger & Bouchard 2012; MOFA 2018 Suppl.
+                           | mofa_ref_general)                                  | "Non-gaussian likelihoods"; mofapy2
+                           |                                                   | PseudoY_Seeger / Tau_Seeger nodes [recalled]
+  convergence              | |dELBO| / |ELBO_0| * 100 < {fast 5e-4, medium 5e-5,| entry_point.set_train_options [recalled]
+                           | slow 5e-6} (%), checked every iteration from the 2nd|
+  factor order on output   | by total variance explained, descending            | implied by tests/test_muon_tools.py:42-44
+  ELBO                     | every term verified against a dense term-by-term   | tests/test_oracle_mofa.py::
+                           | evaluation from the posterior moments              | test_elbo_equals_bruteforce_dense_evaluation
+
 Model (gaussian views m, one group, no missing values):
     y_nd = sum_k z_nk w_dk + eps,  eps ~ N(0, 1/tau_d)
     z_nk ~ N(0, 1/alphaZ_k)                      (ard_factors; fixed N(0,1) otherwise)

@@ -276,7 +276,8 @@ def test_tiled_reduce_equals_atomic_reduce_and_counts_feed_the_transposition(cud
     for (a0, a1, Ta), (b0, b1, Tb) in zip(Tp.panels, Tq.panels):
         assert (a0, a1) == (b0, b1) and torch.equal(Ta.indptr, Tb.indptr)
         Y = torch.randn((a1 - a0, 64), device=cuda)
-        np.testing.assert_allclose(_device.spmm(Ta, Y).cpu().numpy(), _device.spmm(Tb, Y).cpu().numpy(), rtol=1e-4, atol=1e-5)
+        ya, yb = _device.spmm(Ta, Y).cpu().numpy(), _device.spmm(Tb, Y).cpu().numpy()
+        assert np.abs(ya - yb).max() <= 1e-5 * np.abs(yb).max()       # same entry sets, different summation order
     # binarize fused, float sums exact
     gb = _device.tfidf_csr(A, binarize=True)
     monkeypatch.setenv("MUON_B200_TFIDF_TILED", "0")
