@@ -88,17 +88,24 @@ class Stager:
         except Exception:
             pass
 
-    def h2d(self, src: np.ndarray, dst: torch.Tensor, narrow: bool = False, want_hash: bool = False, stream=None):
-        """src: contiguous 1-D host array -> dst (device tensor of the same length; int32 when ``narrow``)."""
+    def h2d(self, src: np.ndarray, dst: torch.Tensor, narrow=False, want_hash: bool = False, stream=None):
+        """src: contiguous 1-D host array -> dst (device tensor of the same length).  ``narrow``: True / 1 = int64 ->
+        int32 (dst int32); 2 = float32 -> uint8 for count data (dst uint8; returns False instead of raising if a
+        value is not an integer in [0, 255] -- the caller resends the block as float32)."""
         C = self._C
         h, ov = C.c_uint64(0), C.c_int32(0)
         assert src.flags.c_contiguous and dst.is_contiguous() and src.shape[0] == dst.numel()
+        mode = int(narrow)
         eb = src.itemsize if src.itemsize in (4, 8) else 1
         n = src.shape[0] if eb != 1 else src.nbytes
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
         with _timed("h2d_s"):
-            call("mub_stager_h2d", self.handle, src.ctypes.data, dst.data_ptr(), n, eb, 1 if narrow else 0,
+            call("mub_stager_h2d", self.handle, src.ctypes.data, dst.data_ptr(), n, eb, mode,
                  C.byref(h) if want_hash else None, C.byref(ov), st)
+        if HOST_TIMES is not None:
+            HOST_TIMES["h2d_bytes"] = HOST_TIMES.get("h2d_bytes", 0) + dst.numel() * dst.element_size()
+        if mode == 2:
+            return not ov.value
         if ov.value:
             raise MuonB200Error("column index does not fit int32 (n_vars >= 2^31 is not supported)")
         return h.value if want_hash else None
@@ -111,6 +118,8 @@ class Stager:
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
         with _timed("d2h_s"):
             call("mub_stager_d2h", self.handle, src.data_ptr(), dst.ctypes.data, nbytes, C.byref(h) if want_hash else None, st)
+        if HOST_TIMES is not None:
+            HOST_TIMES["d2h_bytes"] = HOST_TIMES.get("d2h_bytes", 0) + nbytes
         return h.value if want_hash else None
 
     def fingerprint(self, a: np.ndarray) -> int:
@@ -709,9 +718,19 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     narrow = indices_h.dtype == np.int64
     assert narrow or indices_h.dtype == np.int32, indices_h.dtype
     fp_idx, fp_out = [], []
+    # peak counts are small integers stored as float32: they cross the bus as uint8 (a quarter of the bytes) and are
+    # widened on the device; the first block that holds anything else switches this off for the rest of the matrix
+    as_u8 = os.environ.get("MUON_B200_COUNTS_U8", "1") != "0"
+    tmp8 = torch.empty(max(k1 - k0 for (_, _, k0, k1) in blocks), dtype=torch.uint8, device=dev) if (as_u8 and blocks) else None
+    if tmp8 is not None:
+        tmp8.record_stream(side)
     for (r0, r1, k0, k1) in blocks:
         st.h2d(indices_h[k0:k1], indices[k0:k1], narrow=narrow, stream=side)
-        st.h2d(data_h[k0:k1], data[k0:k1], stream=side)
+        if as_u8 and st.h2d(data_h[k0:k1], tmp8[:k1 - k0], narrow=2, stream=side):
+            call("mub_u8_to_f32", ptr(tmp8), k1 - k0, ptr(data) + 4 * k0, side.cuda_stream)
+        else:
+            as_u8 = False
+            st.h2d(data_h[k0:k1], data[k0:k1], stream=side)
         main.wait_event(side.record_event())
         if tiled:      # host matrices must be canonical anyway (checked here): sorted rows, so the tiled pass applies
             call("mub_tfidf_reduce_tiled_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,

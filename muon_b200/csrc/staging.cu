@@ -71,6 +71,19 @@ MUB_SIMD_CLONES static uint64_t hash_run_i64(const int64_t* src, size_t n, uint6
     return h;
 }
 
+// float32 -> uint8 for count data (peak counts are "mostly 1 and 2"): a quarter of the bytes on the bus.  Returns
+// non-zero if some value is not an integer in [0, 255] (the caller then sends the block as it is).
+MUB_SIMD_CLONES static int narrow_f32_u8(uint8_t* dst, const float* src, size_t n) {
+    int bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float v = src[i];
+        const int iv = (v >= 0.f && v <= 255.f) ? (int)v : -1;
+        bad |= (iv < 0) | ((float)iv != v);
+        dst[i] = (uint8_t)iv;
+    }
+    return bad;
+}
+
 static uint64_t hash_only(const void* src, size_t n, int elem_bytes, uint64_t pos0) {
     uint64_t h = 0;
     size_t done = 0;
@@ -238,14 +251,15 @@ int mub_stager_h2d(void* handle, const void* src_h, void* dst, size_t n_elems, i
     using namespace mub;
     MUB_REQUIRE(handle != nullptr && ((mub::Stager*)handle)->n_bufs >= 2, "stager_h2d: stager has no staging buffers");
     MUB_REQUIRE(src_elem_bytes == 4 || src_elem_bytes == 8 || src_elem_bytes == 1, "stager_h2d: element size must be 1, 4 or 8");
-    MUB_REQUIRE(!narrow || src_elem_bytes == 8, "stager_h2d: narrowing needs 8-byte source elements");
-    MUB_REQUIRE(!hash_h || src_elem_bytes == 4 || narrow, "stager_h2d: fingerprint needs 32-bit elements");
+    MUB_REQUIRE(narrow == 0 || (narrow == 1 && src_elem_bytes == 8) || (narrow == 2 && src_elem_bytes == 4),
+                "stager_h2d: narrow = 1 (int64 -> int32) needs 8-byte, narrow = 2 (float32 -> uint8) 4-byte source elements");
+    MUB_REQUIRE(!hash_h || (src_elem_bytes == 4 && narrow == 0) || narrow == 1, "stager_h2d: fingerprint needs 32-bit elements");
     if (hash_h) *hash_h = 0;
     if (n_elems == 0) return 0;
     MUB_REQUIRE(src_h && dst, "stager_h2d: null pointer");
     auto* s = (Stager*)handle;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t dst_elem = narrow ? 4 : (size_t)src_elem_bytes;
+    const size_t dst_elem = narrow == 1 ? 4 : (narrow == 2 ? 1 : (size_t)src_elem_bytes);
     const size_t per_chunk = s->buf_bytes / dst_elem;
     const int T = s->pool->size();
     std::vector<uint64_t> partial(T, 0);
@@ -269,14 +283,16 @@ int mub_stager_h2d(void* handle, const void* src_h, void* dst, size_t n_elems, i
             const size_t i0 = (size_t)p * per;
             if (i0 >= cnt) { partial[p] = 0; return; }
             const size_t m = cnt - i0 < per ? cnt - i0 : per;
-            if (narrow) {
+            if (narrow == 1) {
                 if (narrow_i64((int32_t*)stage + i0, (const int64_t*)src + i0, m)) overflow = 1;
+            } else if (narrow == 2) {
+                if (narrow_f32_u8((uint8_t*)stage + i0, (const float*)src + i0, m)) overflow = 1;
             } else {
                 memcpy(stage + i0 * src_elem_bytes, src + i0 * src_elem_bytes, m * src_elem_bytes);
             }
             // fingerprints are normally taken on the DEVICE copy (mub_device_fingerprint, ~10 ms for 24 GB); the
             // host-side variant costs a second pass over the chunk while it is hot in cache
-            partial[p] = hash_h ? hash_only(narrow ? (const void*)((int32_t*)stage + i0) : (const void*)(stage + i0 * 4), m, 4, off + i0) : 0;
+            partial[p] = hash_h ? hash_only(narrow == 1 ? (const void*)((int32_t*)stage + i0) : (const void*)(stage + i0 * 4), m, 4, off + i0) : 0;
         };
         s->pool->run(fn, parts);
         for (int p = 0; p < parts; ++p) hash += partial[p];
@@ -391,6 +407,39 @@ fingerprint_kernel(const uint32_t* __restrict__ src, int64_t n, unsigned long lo
     if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)h);
 }
 }  // namespace mub
+
+namespace mub {
+__global__ void __launch_bounds__(256)
+u8_to_f32_kernel(const uchar4* __restrict__ src, int64_t n4, float4* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uchar4 v = src[i];
+        dst[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+}
+__global__ void u8_to_f32_tail_kernel(const uint8_t* __restrict__ src, int64_t n, float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+}  // namespace mub
+
+// dst[i] = (float)src[i]: widens count data that crossed the bus as uint8 (mub_stager_h2d narrow = 2)
+extern "C" int mub_u8_to_f32(const void* src, int64_t n, float* dst, mub_stream_t stream) {
+    MUB_REQUIRE(n >= 0, "u8_to_f32: negative size");
+    if (n == 0) return 0;
+    MUB_REQUIRE(src && dst, "u8_to_f32: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = (((uintptr_t)src & 3) == 0) && (((uintptr_t)dst & 15) == 0);
+    const int64_t n4 = vec ? n / 4 : 0;
+    if (n4 > 0) {
+        int64_t want = (n4 + 255) / 256, cap = (int64_t)mub::sm_count() * 8;
+        mub::u8_to_f32_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>((const uchar4*)src, n4, (float4*)dst);
+    }
+    const int64_t rest = n - 4 * n4;
+    if (rest > 0)
+        mub::u8_to_f32_tail_kernel<<<(int)((rest + 255) / 256), 256, 0, s>>>((const uint8_t*)src + 4 * n4, rest, dst + 4 * n4);
+    return mub::check_launch("u8_to_f32");
+}
 
 // Same fingerprint of a device array of n 32-bit elements, ACCUMULATED into *out (device uint64, zero it first).
 extern "C" int mub_device_fingerprint(const void* src, int64_t n, uint64_t* out, mub_stream_t stream) {
