@@ -577,6 +577,45 @@ class TransposedPanels:
                 on_chunk(out[j0:j1])
         return out
 
+    def spmm_rowblocks(self, Y: torch.Tensor, blocks) -> torch.Tensor:
+        """Rows ``blocks`` = [(j0, j1), ...] of A^T Y only, stacked into a compact (sum of block heights) x P buffer
+        (fp32 operand).  Used for the sampled residual check of the LSI driver: 1/16 of the rows costs 1/16 of a pass."""
+        self.wait()
+        P = Y.shape[1]
+        total = sum(j1 - j0 for j0, j1 in blocks)
+        out = torch.empty((total, P), dtype=torch.float32, device=Y.device)
+        o0 = 0
+        for j0, j1 in blocks:
+            first = True
+            for r0, r1, T in self.panels:
+                spmm(T, Y[r0:r1], out=out, accumulate=not first, dynamic=False, rows=(j0, j1, o0))
+                first = False
+            o0 += j1 - j0
+        return out
+
+
+def _row_range(rows, n):
+    """``rows`` of spmm / spmm_h16: None = all rows; (j0, j1) = that row range written to the same rows of ``out``;
+    (j0, j1, o0) = written to out rows starting at o0 (a compact buffer of sampled rows)."""
+    if rows is None:
+        return 0, n, 0
+    if len(rows) == 2:
+        return rows[0], rows[1], rows[0]
+    return rows
+
+
+def sample_row_blocks(d: int, fraction: int = 16, n_blocks: int = 16):
+    """``n_blocks`` evenly spaced contiguous row blocks covering 1/``fraction`` of d rows -> list of (j0, j1)."""
+    bs = max(1, d // (fraction * n_blocks))
+    out, last = [], 0
+    for i in range(n_blocks):
+        j0 = max(last, (i * d) // n_blocks)
+        j1 = min(d, j0 + bs)
+        if j1 > j0:
+            out.append((j0, j1))
+            last = j1
+    return out
+
 
 HALF_SCALE = 32768.0     # 2^15: orthonormal columns (|x| <= 1) stay finite and leave the subnormal range of IEEE half
 
@@ -600,13 +639,13 @@ def spmm_h16(A, Bh: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=Bh.device)
     counter = torch.zeros(1, dtype=torch.int64, device=Bh.device) if dynamic else None
-    j0, j1 = (0, n) if rows is None else rows          # output row range (indptr holds absolute offsets)
+    j0, j1, o0 = _row_range(rows, n)                    # matrix rows [j0, j1) -> out rows [o0, o0 + j1 - j0)
     if isinstance(A, DevicePairs):
-        call("mub_spmm_csrp_h16", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(Bh), P, ptr(out) + 4 * P * j0,
+        call("mub_spmm_csrp_h16", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(Bh), P, ptr(out) + 4 * P * o0,
              1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
     else:
         call("mub_spmm_csr_h16", ptr(A.indptr) + 8 * j0, ptr(A.indices), ptr(A.data), j1 - j0, d, ptr(Bh), P,
-             ptr(out) + 4 * P * j0, 1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
+             ptr(out) + 4 * P * o0, 1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
     return out
 
 
@@ -622,10 +661,10 @@ def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accu
     if out is None:
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=B.device)
-    j0, j1 = (0, n) if rows is None else rows          # output row range (indptr holds absolute offsets)
+    j0, j1, o0 = _row_range(rows, n)                    # matrix rows [j0, j1) -> out rows [o0, o0 + j1 - j0)
     if isinstance(A, DevicePairs):
         counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
-        call("mub_spmm_csrp_f32", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(B), P, ptr(out) + 4 * P * j0,
+        call("mub_spmm_csrp_f32", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(B), P, ptr(out) + 4 * P * o0,
              1 if accumulate else 0, ptr(counter), stream_ptr())
         return out
     if algo is None:
@@ -640,7 +679,7 @@ def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accu
         return out
     counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
     call("mub_spmm_csr_f32", ptr(A.indptr) + 8 * j0, ptr(A.indices), ptr(A.data), j1 - j0, d, ptr(B), P,
-         ptr(out) + 4 * P * j0, 1 if accumulate else 0, ptr(counter), stream_ptr())
+         ptr(out) + 4 * P * o0, 1 if accumulate else 0, ptr(counter), stream_ptr())
     return out
 
 
