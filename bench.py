@@ -453,6 +453,10 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         per = float(dt[0]) / args.e2e_steps
+        if "h2d_bytes" in ht:       # bytes the staging engine actually put on the bus (counts cross as uint8), + indptr
+            h2d = int(ht.pop("h2d_bytes") / args.e2e_steps) + X.indptr.nbytes
+        if "d2h_bytes" in ht:
+            d2h = int(ht.pop("d2h_bytes") / args.e2e_steps) + 4 * k + (0 if ne * k * 4 > (8 << 20) else 4 * ne * k) + (0 if D * k * 4 > (8 << 20) else 4 * D * k)
         bd = {kk: v / args.e2e_steps for kk, v in ht.items()}
         bd.update({"tfidf_call_s": last["tfidf_s"], "lsi_call_s": last["lsi_s"],
                    "host_other_s": max(0.0, per - last["tfidf_s"] - last["lsi_s"])})

@@ -252,9 +252,11 @@ int mub_spmm_csrp_h16(const int64_t* indptr, const int32_t* pairs, int64_t n_row
  * element stream, by which a later call can prove a host array still equals its device twin.
  * Pointers ending in _h are HOST pointers.  A stager is not thread-safe: one transfer at a time.
  *   create : n_bufs pinned buffers of buf_bytes each (n_bufs = 0: thread pool only, no CUDA context needed)
- *   h2d    : src_elem_bytes 1, 4 or 8; narrow != 0 (8-byte sources): int64 -> int32, *overflow_h = 1 if a value
- *            does not fit; hash_h (optional; 4-byte or narrowed sources) receives the fingerprint.  Chunks are
- *            enqueued on `stream`; returns when the last chunk is enqueued.
+ *   h2d    : src_elem_bytes 1, 4 or 8; narrow = 1 (8-byte sources): int64 -> int32; narrow = 2 (4-byte sources):
+ *            float32 -> uint8 for count data (widen on the device with mub_u8_to_f32); *overflow_h = 1 if a value
+ *            does not survive the narrowing (the destination is then garbage: resend without narrowing); hash_h
+ *            (optional; 4-byte sources or narrow = 1) receives the fingerprint.  Chunks are enqueued on `stream`;
+ *            returns when the last chunk is enqueued.
  *   d2h    : synchronous; hash_h (optional, n_bytes % 4 == 0) receives the fingerprint of what was written.
  *   host_fingerprint   : fingerprint of a host array (elem_bytes 4, or 8 = int64 read as narrowed int32).
  *   device_fingerprint : the same function of a device array of n 32-bit elements, ACCUMULATED into *out
@@ -265,6 +267,7 @@ int mub_stager_h2d(void* stager, const void* src_h, void* dst, size_t n_elems, i
                    int32_t narrow, uint64_t* hash_h, int32_t* overflow_h, mub_stream_t stream);
 int mub_stager_d2h(void* stager, const void* src, void* dst_h, size_t n_bytes, uint64_t* hash_h,
                    mub_stream_t stream);
+int mub_u8_to_f32(const void* src, int64_t n, float* dst, mub_stream_t stream);
 int mub_host_fingerprint(void* stager, const void* src_h, size_t n_elems, int32_t elem_bytes, uint64_t* hash_h);
 int mub_device_fingerprint(const void* src, int64_t n, uint64_t* out, mub_stream_t stream);
 

@@ -88,17 +88,24 @@ class Stager:
         except Exception:
             pass
 
-    def h2d(self, src: np.ndarray, dst: torch.Tensor, narrow: bool = False, want_hash: bool = False, stream=None):
-        """src: contiguous 1-D host array -> dst (device tensor of the same length; int32 when ``narrow``)."""
+    def h2d(self, src: np.ndarray, dst: torch.Tensor, narrow=False, want_hash: bool = False, stream=None):
+        """src: contiguous 1-D host array -> dst (device tensor of the same length).  ``narrow``: True / 1 = int64 ->
+        int32 (dst int32); 2 = float32 -> uint8 for count data (dst uint8; returns False instead of raising if a
+        value is not an integer in [0, 255] -- the caller resends the block as float32)."""
         C = self._C
         h, ov = C.c_uint64(0), C.c_int32(0)
         assert src.flags.c_contiguous and dst.is_contiguous() and src.shape[0] == dst.numel()
+        mode = int(narrow)
         eb = src.itemsize if src.itemsize in (4, 8) else 1
         n = src.shape[0] if eb != 1 else src.nbytes
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
         with _timed("h2d_s"):
-            call("mub_stager_h2d", self.handle, src.ctypes.data, dst.data_ptr(), n, eb, 1 if narrow else 0,
+            call("mub_stager_h2d", self.handle, src.ctypes.data, dst.data_ptr(), n, eb, mode,
                  C.byref(h) if want_hash else None, C.byref(ov), st)
+        if HOST_TIMES is not None:
+            HOST_TIMES["h2d_bytes"] = HOST_TIMES.get("h2d_bytes", 0) + dst.numel() * dst.element_size()
+        if mode == 2:
+            return not ov.value
         if ov.value:
             raise MuonB200Error("column index does not fit int32 (n_vars >= 2^31 is not supported)")
         return h.value if want_hash else None
@@ -111,6 +118,8 @@ class Stager:
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
         with _timed("d2h_s"):
             call("mub_stager_d2h", self.handle, src.data_ptr(), dst.ctypes.data, nbytes, C.byref(h) if want_hash else None, st)
+        if HOST_TIMES is not None:
+            HOST_TIMES["d2h_bytes"] = HOST_TIMES.get("d2h_bytes", 0) + nbytes
         return h.value if want_hash else None
 
     def fingerprint(self, a: np.ndarray) -> int:
@@ -568,6 +577,45 @@ class TransposedPanels:
                 on_chunk(out[j0:j1])
         return out
 
+    def spmm_rowblocks(self, Y: torch.Tensor, blocks) -> torch.Tensor:
+        """Rows ``blocks`` = [(j0, j1), ...] of A^T Y only, stacked into a compact (sum of block heights) x P buffer
+        (fp32 operand).  Used for the sampled residual check of the LSI driver: 1/16 of the rows costs 1/16 of a pass."""
+        self.wait()
+        P = Y.shape[1]
+        total = sum(j1 - j0 for j0, j1 in blocks)
+        out = torch.empty((total, P), dtype=torch.float32, device=Y.device)
+        o0 = 0
+        for j0, j1 in blocks:
+            first = True
+            for r0, r1, T in self.panels:
+                spmm(T, Y[r0:r1], out=out, accumulate=not first, dynamic=False, rows=(j0, j1, o0))
+                first = False
+            o0 += j1 - j0
+        return out
+
+
+def _row_range(rows, n):
+    """``rows`` of spmm / spmm_h16: None = all rows; (j0, j1) = that row range written to the same rows of ``out``;
+    (j0, j1, o0) = written to out rows starting at o0 (a compact buffer of sampled rows)."""
+    if rows is None:
+        return 0, n, 0
+    if len(rows) == 2:
+        return rows[0], rows[1], rows[0]
+    return rows
+
+
+def sample_row_blocks(d: int, fraction: int = 16, n_blocks: int = 16):
+    """``n_blocks`` evenly spaced contiguous row blocks covering 1/``fraction`` of d rows -> list of (j0, j1)."""
+    bs = max(1, d // (fraction * n_blocks))
+    out, last = [], 0
+    for i in range(n_blocks):
+        j0 = max(last, (i * d) // n_blocks)
+        j1 = min(d, j0 + bs)
+        if j1 > j0:
+            out.append((j0, j1))
+            last = j1
+    return out
+
 
 HALF_SCALE = 32768.0     # 2^15: orthonormal columns (|x| <= 1) stay finite and leave the subnormal range of IEEE half
 
@@ -591,13 +639,13 @@ def spmm_h16(A, Bh: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=Bh.device)
     counter = torch.zeros(1, dtype=torch.int64, device=Bh.device) if dynamic else None
-    j0, j1 = (0, n) if rows is None else rows          # output row range (indptr holds absolute offsets)
+    j0, j1, o0 = _row_range(rows, n)                    # matrix rows [j0, j1) -> out rows [o0, o0 + j1 - j0)
     if isinstance(A, DevicePairs):
-        call("mub_spmm_csrp_h16", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(Bh), P, ptr(out) + 4 * P * j0,
+        call("mub_spmm_csrp_h16", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(Bh), P, ptr(out) + 4 * P * o0,
              1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
     else:
         call("mub_spmm_csr_h16", ptr(A.indptr) + 8 * j0, ptr(A.indices), ptr(A.data), j1 - j0, d, ptr(Bh), P,
-             ptr(out) + 4 * P * j0, 1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
+             ptr(out) + 4 * P * o0, 1 if accumulate else 0, 1.0 / scale, ptr(counter), stream_ptr())
     return out
 
 
@@ -613,10 +661,10 @@ def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accu
     if out is None:
         assert not accumulate
         out = torch.empty((n, P), dtype=torch.float32, device=B.device)
-    j0, j1 = (0, n) if rows is None else rows          # output row range (indptr holds absolute offsets)
+    j0, j1, o0 = _row_range(rows, n)                    # matrix rows [j0, j1) -> out rows [o0, o0 + j1 - j0)
     if isinstance(A, DevicePairs):
         counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
-        call("mub_spmm_csrp_f32", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(B), P, ptr(out) + 4 * P * j0,
+        call("mub_spmm_csrp_f32", ptr(A.indptr) + 8 * j0, ptr(A.pairs), j1 - j0, d, ptr(B), P, ptr(out) + 4 * P * o0,
              1 if accumulate else 0, ptr(counter), stream_ptr())
         return out
     if algo is None:
@@ -631,7 +679,7 @@ def spmm(A: DeviceCSR, B: torch.Tensor, out: Optional[torch.Tensor] = None, accu
         return out
     counter = torch.zeros(1, dtype=torch.int64, device=B.device) if dynamic else None
     call("mub_spmm_csr_f32", ptr(A.indptr) + 8 * j0, ptr(A.indices), ptr(A.data), j1 - j0, d, ptr(B), P,
-         ptr(out) + 4 * P * j0, 1 if accumulate else 0, ptr(counter), stream_ptr())
+         ptr(out) + 4 * P * o0, 1 if accumulate else 0, ptr(counter), stream_ptr())
     return out
 
 
@@ -709,9 +757,19 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     narrow = indices_h.dtype == np.int64
     assert narrow or indices_h.dtype == np.int32, indices_h.dtype
     fp_idx, fp_out = [], []
+    # peak counts are small integers stored as float32: they cross the bus as uint8 (a quarter of the bytes) and are
+    # widened on the device; the first block that holds anything else switches this off for the rest of the matrix
+    as_u8 = os.environ.get("MUON_B200_COUNTS_U8", "1") != "0"
+    tmp8 = torch.empty(max(k1 - k0 for (_, _, k0, k1) in blocks), dtype=torch.uint8, device=dev) if (as_u8 and blocks) else None
+    if tmp8 is not None:
+        tmp8.record_stream(side)
     for (r0, r1, k0, k1) in blocks:
         st.h2d(indices_h[k0:k1], indices[k0:k1], narrow=narrow, stream=side)
-        st.h2d(data_h[k0:k1], data[k0:k1], stream=side)
+        if as_u8 and st.h2d(data_h[k0:k1], tmp8[:k1 - k0], narrow=2, stream=side):
+            call("mub_u8_to_f32", ptr(tmp8), k1 - k0, ptr(data) + 4 * k0, side.cuda_stream)
+        else:
+            as_u8 = False
+            st.h2d(data_h[k0:k1], data[k0:k1], stream=side)
         main.wait_event(side.record_event())
         if tiled:      # host matrices must be canonical anyway (checked here): sorted rows, so the tiled pass applies
             call("mub_tfidf_reduce_tiled_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,

@@ -57,6 +57,7 @@ SIGNATURES = {
     "mub_stager_destroy": [vp],
     "mub_stager_h2d": [vp, vp, vp, C.c_size_t, i32, i32, C.POINTER(u64), C.POINTER(i32), vp],
     "mub_stager_d2h": [vp, vp, vp, C.c_size_t, C.POINTER(u64), vp],
+    "mub_u8_to_f32": [vp, i64, vp, vp],
     "mub_host_fingerprint": [vp, vp, C.c_size_t, i32, C.POINTER(u64)],
     "mub_device_fingerprint": [vp, i64, vp, vp],
     "mub_synth_count": [i64, i64, i32, vp, vp, vp, vp, u64, vp, vp],

@@ -43,6 +43,8 @@ class SvdInfo:
     passes: int = 0              # sparse passes over A or A^T
     lowp_passes: int = 0         # of which with the dense operand rounded to IEEE half
     replica_repairs: int = 0     # multi-GPU: times the replicated d-space block had to be re-broadcast (expected 0)
+    sampled_checks: int = 0      # residual estimates on 1/16 of the peaks (each costs 1/16 of a pass)
+    sampled_stop: bool = False   # convergence was accepted on such an estimate (<= tol/3) instead of a full pass
     iterations: int = 0
     restarts: int = 0
     basis: int = 0
@@ -91,6 +93,19 @@ class CsrOperator:
             return W
 
     AR_CHUNKS = int(os.environ.get("MUON_B200_AR_CHUNKS", "4"))
+
+    def residual_sample(self, Uk, Vk, sig):
+        """Estimate of the relative residuals ||A^T u_i - sigma_i v_i|| / sigma_i of k triplets from 1/16 of the
+        peaks (16 evenly spaced contiguous blocks of rows of A^T): ||r||^2 ~ (d/|S|) * sum_{j in S} r_j^2.  Costs 1/16
+        of a pass; the driver uses it to skip the pass that would only confirm convergence."""
+        blocks = self._dev.sample_row_blocks(self.d)
+        with phase("lsi.residual_sample"):
+            W = self.At.spmm_rowblocks(Uk.contiguous(), blocks)          # Uk: n_local x P (padded by the driver)
+            W = _dist.all_reduce_sum_(W)
+            idx = torch.cat([torch.arange(j0, j1, device=self.device) for j0, j1 in blocks])
+            k = Vk.shape[1]
+            R = W[:, :k].to(torch.float64) - Vk[idx].to(torch.float64) * sig[None, :k]
+            return torch.sqrt((R * R).sum(0) * (self.d / idx.numel())) / sig[:k].clamp_min(1e-300)
 
     def gram(self, Y, l):
         return self._dev.gram(Y, l, reduce=True)
@@ -178,7 +193,7 @@ def _orth_against(W: torch.Tensor, Q: torch.Tensor, passes: int = 2):
 
 def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optional[int] = None,
                   max_restarts: int = 4, seed: int = 0, verbose: bool = False, polish: Optional[bool] = None,
-                  lowp_tol: Optional[float] = None):
+                  lowp_tol: Optional[float] = None, sample_check: Optional[bool] = None):
     """Top-k singular triplets of the (cell-sharded) matrix behind ``op``.
 
     Returns (U [n_local x k] fp32, s [k] fp64, V [d x k] fp32, SvdInfo).  ``pad_to`` is the padded
@@ -196,12 +211,18 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
     fp32 from the Ritz vectors: one fp32 block step takes residuals from ~3e-4 to below 1e-5.  The result is the
     fp32 iteration's own (same stopping rule, same Rayleigh-Ritz tail); only the path to the final subspace is
     cheaper.  ``SvdInfo.lowp_passes`` counts the half-precision passes.
+
+    ``sample_check`` (default: $MUON_B200_LSI_SAMPLE_CHECK, "1"): when the residual history predicts that the next
+    pass over A^T would only confirm convergence, estimate the residuals on 1/16 of the peaks first
+    (``op.residual_sample``) and stop if the estimate is <= tol/2; the full pass is skipped only then.
     """
     if polish is None:
         polish = os.environ.get("MUON_B200_LSI_POLISH", "0") != "0"
     if lowp_tol is None:
         lowp_tol = float(os.environ.get("MUON_B200_LSI_LOWP_TOL", "1e-3") or 0.0)
     lowp = bool(getattr(op, "lowp", False)) and lowp_tol > tol
+    if sample_check is None:
+        sample_check = os.environ.get("MUON_B200_LSI_SAMPLE_CHECK", "1") != "0"
     d, dev, P = op.d, op.device, pad_to
     k = int(k)
     b = min(P, d, getattr(op, "n_total", d))
@@ -236,12 +257,42 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
         Bmat[:b, :b] = R
         blocks = [(0, b)]                      # column ranges of the blocks
         Ublocks = None if (polish or lowp) else [U[:, :b].clone()]   # left Lanczos blocks (only needed without the polish)
-        prev_res, stagn = None, 0
+        prev_res, prev_prev, stagn = None, None, 0
         done = False
         target = lowp_tol if lowp else tol
         while True:
             j0, j1 = blocks[-1]
             bj = j1 - j0
+            # ---- would the next pass only CONFIRM convergence?  After a left update the Ritz triplets of the
+            # current spaces are known without another pass (A V = U B exactly), only their right residual is not;
+            # when the residual history predicts convergence, estimate it on 1/16 of the peaks (op.residual_sample)
+            # and finish if the estimate is at most tol/2 (the estimator's spread over 1/16 of 200k peaks is a few %).  Otherwise (or if the operator cannot sample)
+            # carry on with the full pass, which then decides as before.
+            if (not lowp and Ublocks is not None and len(blocks) >= 2 and prev_res is not None and sample_check
+                    and prev_res * min(prev_res / prev_prev if prev_prev else 0.1, 0.1) <= 3.0 * tol
+                    and hasattr(op, "residual_sample")):
+                with phase("lsi.ritz_svd"):
+                    Bm = Bmat[:m, :m]
+                    lam, Zr = torch.linalg.eigh(Bm.T @ Bm)
+                    kk = min(k, m)
+                    sig = lam.flip(0).clamp_min(0).sqrt()
+                    Zt = Zr.flip(1).T.contiguous()
+                    Vk_try = Vall[:, :m] @ Zt[:kk, :].T.to(torch.float32)
+                    Xl = (Bm @ Zt[:kk, :].T) / sig[:kk].clamp_min(1e-300)
+                    Uk_try = _pad(torch.cat(Ublocks, 1) @ Xl.to(torch.float32), P)
+                est = op.residual_sample(Uk_try, Vk_try, sig[:kk])
+                if _dist.is_distributed():
+                    est = _dist.all_reduce_max_(est.contiguous())
+                info.sampled_checks += 1
+                if float(est.max()) <= tol / 2.0:
+                    rmax = float(est.max())
+                    info.history.append(rmax)
+                    info.residuals = est.tolist()
+                    info.sampled_stop = True
+                    Vk, Uk_lanczos, s_lanczos = Vk_try, Uk_try[:, :kk].contiguous(), sig[:kk].clone()
+                    V0_next = Vk
+                    done = True
+                    break
             # ---- right side: W = A^T U_j - V_j R_j^T, full reorth, QR --------------------
             W = _aty(U)[:, :bj].clone()
             info.passes += 1
@@ -299,7 +350,7 @@ def truncated_svd(op, k: int, pad_to: int, tol: float = 1e-5, max_basis: Optiona
                 stagn += 1
             else:
                 stagn = 0
-            prev_res = rmax
+            prev_prev, prev_res = prev_res, rmax
             if rmax <= target or stagn >= 2 or bn <= 0:
                 done = (rmax <= target) or stagn >= 2 or m >= d
                 info.residuals = res.tolist()

@@ -162,18 +162,20 @@ __device__ __forceinline__ void spmm_row_h(const int32_t* __restrict__ indices, 
     constexpr int STEPS = 32 / G;   // gathers per 32-nnz segment
     const int sub = lane % LPN, grp = lane / LPN;
     const __half* Bl = B + sub * 8;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // accumulators as four packed float2 (64-bit registers): Blackwell's fma.rn.f32x2 retires two fp32 FMAs per
+    // issue slot, and with the half operand this kernel is bound by issue slots (ncu: 65 % issue-active), not by L2
+    unsigned long long acc2[4] = {0ull, 0ull, 0ull, 0ull};
     auto fma8 = [&](float v, const uint4& q) {
-        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
-        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&q.z));
-        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&q.w));
-        acc[0] = fmaf(v, f0.x, acc[0]); acc[1] = fmaf(v, f0.y, acc[1]);
-        acc[2] = fmaf(v, f1.x, acc[2]); acc[3] = fmaf(v, f1.y, acc[3]);
-        acc[4] = fmaf(v, f2.x, acc[4]); acc[5] = fmaf(v, f2.y, acc[5]);
-        acc[6] = fmaf(v, f3.x, acc[6]); acc[7] = fmaf(v, f3.y, acc[7]);
+        unsigned long long vv2;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(vv2) : "f"(v));
+        const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            unsigned long long b2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(f.x), "f"(f.y));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i]) : "l"(vv2), "l"(b2));
+        }
     };
     int64_t base = start;
     // the (index, value) stream comes from HBM (~600 ns), the gathers from L2 (~130 ns): fetch the NEXT segment's
@@ -213,6 +215,9 @@ __device__ __forceinline__ void spmm_row_h(const int32_t* __restrict__ indices, 
             if (src < cnt) fma8(vt, ld_gather_u4(Bl + (size_t)cc * P));
         }
     }
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i]), "=f"(acc[2 * i + 1]) : "l"(acc2[i]));
 #pragma unroll
     for (int off = LPN; off < 32; off <<= 1) {
 #pragma unroll

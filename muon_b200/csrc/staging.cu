@@ -71,6 +71,19 @@ MUB_SIMD_CLONES static uint64_t hash_run_i64(const int64_t* src, size_t n, uint6
     return h;
 }
 
+// float32 -> uint8 for count data (peak counts are "mostly 1 and 2"): a quarter of the bytes on the bus.  Returns
+// non-zero if some value is not an integer in [0, 255] (the caller then sends the block as it is).
+MUB_SIMD_CLONES static int narrow_f32_u8(uint8_t* dst, const float* src, size_t n) {
+    int bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float v = src[i];
+        const int iv = (v >= 0.f && v <= 255.f) ? (int)v : -1;
+        bad |= (iv < 0) | ((float)iv != v);
+        dst[i] = (uint8_t)iv;
+    }
+    return bad;
+}
+
 static uint64_t hash_only(const void* src, size_t n, int elem_bytes, uint64_t pos0) {
     uint64_t h = 0;
     size_t done = 0;
@@ -170,11 +183,19 @@ class Pool {
 };
 
 struct Stager {
-    size_t buf_bytes = 0;
+    size_t buf_bytes = 0;       // bytes per ring buffer
     int n_bufs = 0;
-    std::vector<void*> bufs;
-    std::vector<cudaEvent_t> events;
+    int device = 0;             // CUDA device the ring and the events belong to
+    std::vector<void*> bufs;    // the ring is used as n_threads x 2 private sub-buffers (see stage_of)
+    std::vector<cudaEvent_t> events;   // one per (thread, sub-buffer)
     Pool* pool = nullptr;
+    size_t sub_bytes = 0;
+
+    // sub-buffer j (0/1) of worker t: the ring is one logical array of n_bufs * buf_bytes bytes cut into 2T pieces
+    char* stage_of(int t, int j) const {
+        const size_t idx = (size_t)(2 * t + j) * sub_bytes;
+        return (char*)bufs[idx / buf_bytes] + idx % buf_bytes;
+    }
 };
 
 #define MUB_CUDA(call, what)                                          \
@@ -193,26 +214,41 @@ extern "C" {
 int mub_stager_create(size_t buf_bytes, int32_t n_bufs, int32_t n_threads, void** out) {
     MUB_REQUIRE(out != nullptr, "stager_create: null out");
     // n_bufs == 0: thread pool only (host fingerprints; needs no CUDA context)
-    MUB_REQUIRE(buf_bytes >= 4096 && (buf_bytes % 16) == 0 && (n_bufs == 0 || (n_bufs >= 2 && n_bufs <= 64)) && n_threads >= 1,
-                "stager_create: need buf_bytes >= 4096 (multiple of 16), 0 or 2..64 buffers, >=1 thread");
+    MUB_REQUIRE(buf_bytes >= 4096 && (buf_bytes % 4096) == 0 && (n_bufs == 0 || (n_bufs >= 2 && n_bufs <= 64)) && n_threads >= 1,
+                "stager_create: need buf_bytes >= 4096 (multiple of 4096), 0 or 2..64 buffers, >=1 thread");
     auto* s = new mub::Stager();
     s->buf_bytes = buf_bytes;
     s->n_bufs = n_bufs;
+    if (n_bufs > 0) {
+        cudaGetDevice(&s->device);
+        // every worker owns two sub-buffers; a sub-buffer must not straddle two ring buffers
+        size_t sub = (buf_bytes * (size_t)n_bufs) / (2 * (size_t)n_threads);
+        sub &= ~(size_t)4095;
+        while (sub >= 4096 && (buf_bytes % sub) != 0) sub -= 4096;
+        if (sub < 4096) {
+            mub::set_error("stager_create: %d threads need a larger staging ring than %zu bytes", n_threads, buf_bytes * n_bufs);
+            delete s;
+            return -1;
+        }
+        s->sub_bytes = sub;
+    }
     for (int i = 0; i < n_bufs; ++i) {
         void* p = nullptr;
         cudaError_t e = cudaHostAlloc(&p, buf_bytes, cudaHostAllocDefault);
         if (e != cudaSuccess) {
             mub::set_error("stager_create: cudaHostAlloc(%zu): %s", buf_bytes, cudaGetErrorString(e));
             for (void* q : s->bufs) cudaFreeHost(q);
-            for (auto ev : s->events) cudaEventDestroy(ev);
             delete s;
             return -2;
         }
         s->bufs.push_back(p);
-        cudaEvent_t ev;
-        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        s->events.push_back(ev);
     }
+    if (n_bufs > 0)
+        for (int i = 0; i < 2 * n_threads; ++i) {
+            cudaEvent_t ev;
+            cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            s->events.push_back(ev);
+        }
     s->pool = new mub::Pool(n_threads);
     *out = s;
     return 0;
@@ -228,69 +264,78 @@ int mub_stager_destroy(void* handle) {
     return 0;
 }
 
-// Pageable host -> device.  src_elem_bytes: 4 or 8 (bytes of one source element);  narrow != 0 (only with
-// 8-byte sources): int64 -> int32 on the host while staging; a value outside int32 sets *overflow_h.
-// hash_h (optional): fingerprint of the uploaded stream as 32-bit elements (4-byte sources, or narrowed
-// 8-byte sources).  All chunks are enqueued on `stream`; returns once the last chunk is enqueued (the
-// staging buffers are guarded by events, so the call may be followed by another one immediately).
+// Pageable host -> device.  src_elem_bytes: 1, 4 or 8 (bytes of one source element);  narrow = 1 (8-byte sources):
+// int64 -> int32; narrow = 2 (4-byte sources): float32 -> uint8; a value that does not survive sets *overflow_h.
+// hash_h (optional): fingerprint of the uploaded stream as 32-bit elements (4-byte sources, or narrow = 1).
+// The array is cut into one contiguous slab per worker thread; every worker converts its slab piece by piece into
+// its two private pinned sub-buffers and enqueues the DMA of each piece on `stream` itself (the runtime API is
+// thread-safe; copies of different workers interleave on the stream).  One wake-up of the pool per CALL -- an
+// earlier version synchronised the pool once per 64 MB chunk and stopped scaling at 16 threads
+// (profiles/staging_probe_r2.json).  Returns when the last piece is enqueued.
 int mub_stager_h2d(void* handle, const void* src_h, void* dst, size_t n_elems, int32_t src_elem_bytes, int32_t narrow,
                    uint64_t* hash_h, int32_t* overflow_h, mub_stream_t stream) {
     using namespace mub;
     MUB_REQUIRE(handle != nullptr && ((mub::Stager*)handle)->n_bufs >= 2, "stager_h2d: stager has no staging buffers");
     MUB_REQUIRE(src_elem_bytes == 4 || src_elem_bytes == 8 || src_elem_bytes == 1, "stager_h2d: element size must be 1, 4 or 8");
-    MUB_REQUIRE(!narrow || src_elem_bytes == 8, "stager_h2d: narrowing needs 8-byte source elements");
-    MUB_REQUIRE(!hash_h || src_elem_bytes == 4 || narrow, "stager_h2d: fingerprint needs 32-bit elements");
+    MUB_REQUIRE(narrow == 0 || (narrow == 1 && src_elem_bytes == 8) || (narrow == 2 && src_elem_bytes == 4),
+                "stager_h2d: narrow = 1 (int64 -> int32) needs 8-byte, narrow = 2 (float32 -> uint8) 4-byte source elements");
+    MUB_REQUIRE(!hash_h || (src_elem_bytes == 4 && narrow == 0) || narrow == 1, "stager_h2d: fingerprint needs 32-bit elements");
     if (hash_h) *hash_h = 0;
     if (n_elems == 0) return 0;
     MUB_REQUIRE(src_h && dst, "stager_h2d: null pointer");
     auto* s = (Stager*)handle;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t dst_elem = narrow ? 4 : (size_t)src_elem_bytes;
-    const size_t per_chunk = s->buf_bytes / dst_elem;
+    const size_t dst_elem = narrow == 1 ? 4 : (narrow == 2 ? 1 : (size_t)src_elem_bytes);
     const int T = s->pool->size();
-    std::vector<uint64_t> partial(T, 0);
-    int overflow = 0;
-    uint64_t hash = 0;
-    size_t off = 0;
-    for (size_t c = 0; off < n_elems; ++c, off += per_chunk) {
-        const int b = (int)(c % s->n_bufs);
-        const size_t cnt = n_elems - off < per_chunk ? n_elems - off : per_chunk;
-        // the buffer may still feed a DMA of this or of an earlier transfer (possibly on another stream); an event
-        // that was never recorded is complete by definition
-        MUB_CUDA(cudaEventSynchronize(s->events[b]), "stager_h2d: event sync");
-        char* stage = (char*)s->bufs[b];
-        const char* src = (const char*)src_h + off * (size_t)src_elem_bytes;
-        // split the chunk over the pool in 64-byte aligned parts
-        const size_t gran = 4096;
-        int parts = (int)((cnt + gran - 1) / gran);
-        if (parts > T) parts = T;
-        const size_t per = ((cnt + parts - 1) / parts + 15) & ~(size_t)15;
-        std::function<void(int)> fn = [&](int p) {
-            const size_t i0 = (size_t)p * per;
-            if (i0 >= cnt) { partial[p] = 0; return; }
-            const size_t m = cnt - i0 < per ? cnt - i0 : per;
-            if (narrow) {
-                if (narrow_i64((int32_t*)stage + i0, (const int64_t*)src + i0, m)) overflow = 1;
+    // slabs of whole 64-element groups; small arrays use fewer workers
+    size_t groups = (n_elems + 63) / 64;
+    int workers = (int)(groups < (size_t)T * 1024 ? (groups + 1023) / 1024 : T);
+    if (workers < 1) workers = 1;
+    const size_t slab = ((groups + workers - 1) / workers) * 64;
+    const size_t per_piece = s->sub_bytes / dst_elem;   // elements per sub-buffer (the staged, converted form)
+    std::vector<uint64_t> partial(workers, 0);
+    std::atomic<int> overflow{0}, failed{0};
+    std::function<void(int)> fn = [&](int t) {
+        cudaSetDevice(s->device);
+        const size_t lo = (size_t)t * slab, hi = lo + slab < n_elems ? lo + slab : n_elems;
+        uint64_t h = 0;
+        int j = 0;
+        for (size_t off = lo; off < hi; off += per_piece, j ^= 1) {
+            const size_t cnt = hi - off < per_piece ? hi - off : per_piece;
+            char* stage = s->stage_of(t, j);
+            if (cudaEventSynchronize(s->events[2 * t + j]) != cudaSuccess) { failed = 1; return; }
+            const char* src = (const char*)src_h + off * (size_t)src_elem_bytes;
+            if (narrow == 1) {
+                if (narrow_i64((int32_t*)stage, (const int64_t*)src, cnt)) overflow = 1;
+            } else if (narrow == 2) {
+                if (narrow_f32_u8((uint8_t*)stage, (const float*)src, cnt)) overflow = 1;
             } else {
-                memcpy(stage + i0 * src_elem_bytes, src + i0 * src_elem_bytes, m * src_elem_bytes);
+                memcpy(stage, src, cnt * (size_t)src_elem_bytes);
             }
-            // fingerprints are normally taken on the DEVICE copy (mub_device_fingerprint, ~10 ms for 24 GB); the
-            // host-side variant costs a second pass over the chunk while it is hot in cache
-            partial[p] = hash_h ? hash_only(narrow ? (const void*)((int32_t*)stage + i0) : (const void*)(stage + i0 * 4), m, 4, off + i0) : 0;
-        };
-        s->pool->run(fn, parts);
-        for (int p = 0; p < parts; ++p) hash += partial[p];
-        MUB_CUDA(cudaMemcpyAsync((char*)dst + off * dst_elem, stage, cnt * dst_elem, cudaMemcpyHostToDevice, st),
-                 "stager_h2d: cudaMemcpyAsync");
-        MUB_CUDA(cudaEventRecord(s->events[b], st), "stager_h2d: event record");
+            if (hash_h) h += hash_only(stage, cnt, 4, off);
+            if (cudaMemcpyAsync((char*)dst + off * dst_elem, stage, cnt * dst_elem, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                cudaEventRecord(s->events[2 * t + j], st) != cudaSuccess) { failed = 1; return; }
+        }
+        partial[t] = h;
+    };
+    s->pool->run(fn, workers);
+    if (failed.load()) {
+        cudaError_t e = cudaGetLastError();
+        set_error("stager_h2d: %s", cudaGetErrorString(e));
+        return -2;
     }
-    if (hash_h) *hash_h = hash;
-    if (overflow_h && overflow) *overflow_h = 1;
+    if (hash_h) {
+        uint64_t h = 0;
+        for (int t = 0; t < workers; ++t) h += partial[t];
+        *hash_h = h;
+    }
+    if (overflow_h && overflow.load()) *overflow_h = 1;
     return 0;
 }
 
 // Device -> pageable host, n_bytes (multiple of 4 when a fingerprint is requested).  Synchronous with respect to
-// the host: returns when dst_h is complete.  hash_h: fingerprint of the downloaded 32-bit element stream.
+// the host: returns when dst_h is complete.  Same slab-per-worker scheme as mub_stager_h2d, each worker
+// double-buffered: the DMA of its next piece runs while it copies the previous one out of pinned memory.
 int mub_stager_d2h(void* handle, const void* src, void* dst_h, size_t n_bytes, uint64_t* hash_h, mub_stream_t stream) {
     using namespace mub;
     MUB_REQUIRE(handle != nullptr && ((mub::Stager*)handle)->n_bufs >= 2, "stager_d2h: stager has no staging buffers");
@@ -300,47 +345,48 @@ int mub_stager_d2h(void* handle, const void* src, void* dst_h, size_t n_bytes, u
     MUB_REQUIRE(src && dst_h, "stager_d2h: null pointer");
     auto* s = (Stager*)handle;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t per_chunk = s->buf_bytes;
-    const size_t n_chunks = (n_bytes + per_chunk - 1) / per_chunk;
     const int T = s->pool->size();
-    std::vector<uint64_t> partial(T, 0);
-    uint64_t hash = 0;
-    auto issue = [&](size_t c) -> int {
-        const int b = (int)(c % s->n_bufs);
-        const size_t off = c * per_chunk;
-        const size_t cnt = n_bytes - off < per_chunk ? n_bytes - off : per_chunk;
-        MUB_CUDA(cudaEventSynchronize(s->events[b]), "stager_d2h: event sync");   // earlier transfer still reading it?
-        MUB_CUDA(cudaMemcpyAsync(s->bufs[b], (const char*)src + off, cnt, cudaMemcpyDeviceToHost, st),
-                 "stager_d2h: cudaMemcpyAsync");
-        MUB_CUDA(cudaEventRecord(s->events[b], st), "stager_d2h: event record");
-        return 0;
-    };
-    for (size_t c = 0; c < n_chunks && c < (size_t)s->n_bufs; ++c)
-        if (int rc = issue(c)) return rc;
-    for (size_t c = 0; c < n_chunks; ++c) {
-        const int b = (int)(c % s->n_bufs);
-        const size_t off = c * per_chunk;
-        const size_t cnt = n_bytes - off < per_chunk ? n_bytes - off : per_chunk;
-        MUB_CUDA(cudaEventSynchronize(s->events[b]), "stager_d2h: event sync");
-        const char* stage = (const char*)s->bufs[b];
-        char* dst = (char*)dst_h + off;
-        const size_t gran = 16384;
-        int parts = (int)((cnt + gran - 1) / gran);
-        if (parts > T) parts = T;
-        const size_t per = ((cnt + parts - 1) / parts + 63) & ~(size_t)63;
-        std::function<void(int)> fn = [&](int p) {
-            const size_t i0 = (size_t)p * per;
-            if (i0 >= cnt) { partial[p] = 0; return; }
-            const size_t m = cnt - i0 < per ? cnt - i0 : per;
-            memcpy(dst + i0, stage + i0, m);
-            partial[p] = hash_h ? hash_only(stage + i0, m / 4, 4, (off + i0) / 4) : 0;
+    size_t groups = (n_bytes + 4095) / 4096;
+    int workers = (int)(groups < (size_t)T * 64 ? (groups + 63) / 64 : T);
+    if (workers < 1) workers = 1;
+    const size_t slab = ((groups + workers - 1) / workers) * 4096;
+    const size_t per_piece = s->sub_bytes;
+    std::vector<uint64_t> partial(workers, 0);
+    std::atomic<int> failed{0};
+    std::function<void(int)> fn = [&](int t) {
+        cudaSetDevice(s->device);
+        const size_t lo = (size_t)t * slab, hi = lo + slab < n_bytes ? lo + slab : n_bytes;
+        if (lo >= hi) return;
+        auto issue = [&](size_t off, int j) -> bool {
+            const size_t cnt = hi - off < per_piece ? hi - off : per_piece;
+            // an earlier transfer (possibly on another stream) may still read this sub-buffer
+            return cudaEventSynchronize(s->events[2 * t + j]) == cudaSuccess &&
+                   cudaMemcpyAsync(s->stage_of(t, j), (const char*)src + off, cnt, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                   cudaEventRecord(s->events[2 * t + j], st) == cudaSuccess;
         };
-        s->pool->run(fn, parts);
-        for (int p = 0; p < parts; ++p) hash += partial[p];
-        if (c + s->n_bufs < n_chunks)
-            if (int rc = issue(c + s->n_bufs)) return rc;
+        uint64_t h = 0;
+        int j = 0;
+        if (!issue(lo, 0)) { failed = 1; return; }
+        for (size_t off = lo; off < hi; off += per_piece, j ^= 1) {
+            const size_t cnt = hi - off < per_piece ? hi - off : per_piece;
+            if (off + per_piece < hi && !issue(off + per_piece, j ^ 1)) { failed = 1; return; }
+            if (cudaEventSynchronize(s->events[2 * t + j]) != cudaSuccess) { failed = 1; return; }
+            memcpy((char*)dst_h + off, s->stage_of(t, j), cnt);
+            if (hash_h) h += hash_only(s->stage_of(t, j), cnt / 4, 4, off / 4);
+        }
+        partial[t] = h;
+    };
+    s->pool->run(fn, workers);
+    if (failed.load()) {
+        cudaError_t e = cudaGetLastError();
+        set_error("stager_d2h: %s", cudaGetErrorString(e));
+        return -2;
     }
-    if (hash_h) *hash_h = hash;
+    if (hash_h) {
+        uint64_t h = 0;
+        for (int t = 0; t < workers; ++t) h += partial[t];
+        *hash_h = h;
+    }
     return 0;
 }
 
@@ -391,6 +437,39 @@ fingerprint_kernel(const uint32_t* __restrict__ src, int64_t n, unsigned long lo
     if ((threadIdx.x & 31) == 0) atomicAdd(out, (unsigned long long)h);
 }
 }  // namespace mub
+
+namespace mub {
+__global__ void __launch_bounds__(256)
+u8_to_f32_kernel(const uchar4* __restrict__ src, int64_t n4, float4* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uchar4 v = src[i];
+        dst[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+}
+__global__ void u8_to_f32_tail_kernel(const uint8_t* __restrict__ src, int64_t n, float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+}  // namespace mub
+
+// dst[i] = (float)src[i]: widens count data that crossed the bus as uint8 (mub_stager_h2d narrow = 2)
+extern "C" int mub_u8_to_f32(const void* src, int64_t n, float* dst, mub_stream_t stream) {
+    MUB_REQUIRE(n >= 0, "u8_to_f32: negative size");
+    if (n == 0) return 0;
+    MUB_REQUIRE(src && dst, "u8_to_f32: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = (((uintptr_t)src & 3) == 0) && (((uintptr_t)dst & 15) == 0);
+    const int64_t n4 = vec ? n / 4 : 0;
+    if (n4 > 0) {
+        int64_t want = (n4 + 255) / 256, cap = (int64_t)mub::sm_count() * 8;
+        mub::u8_to_f32_kernel<<<(int)(want < cap ? want : cap), 256, 0, s>>>((const uchar4*)src, n4, (float4*)dst);
+    }
+    const int64_t rest = n - 4 * n4;
+    if (rest > 0)
+        mub::u8_to_f32_tail_kernel<<<(int)((rest + 255) / 256), 256, 0, s>>>((const uint8_t*)src + 4 * n4, rest, dst + 4 * n4);
+    return mub::check_launch("u8_to_f32");
+}
 
 // Same fingerprint of a device array of n 32-bit elements, ACCUMULATED into *out (device uint64, zero it first).
 extern "C" int mub_device_fingerprint(const void* src, int64_t n, uint64_t* out, mub_stream_t stream) {

@@ -178,6 +178,7 @@ tfidf_reduce_tiled_kernel(const int64_t* __restrict__ indptr, const int32_t* __r
                 if (stop || k >= e) break;
             }
             acc = warp_sum(acc);
+            __syncwarp();      // every lane has read cur[r] (racecheck: intra-warp write-after-read without this)
             if (lane == 0) {
                 cur[r] = (int)(k - s0);
                 rsum[r] += acc;

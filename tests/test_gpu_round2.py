@@ -221,6 +221,15 @@ def test_host_path_pipeline_blocks_and_twin_validation(cuda, monkeypatch):
         assert _device.recall_resident(ad.X) is None
         ad.X.indices[5000] = j
         assert _device.recall_resident(ad.X) is not None
+    # values that are not small integers take the float32 route over the bus (first block decides), same result
+    H = C.copy()
+    H.data = (H.data * np.float32(0.5)).astype(np.float32)
+    np.testing.assert_array_equal(mu.atac.pp.tfidf(SimpleAnnData(H.copy()), inplace=False).data,
+                                  _device.tfidf_csr(mu.DeviceCSR.from_scipy(H)).get().data)
+    Hm = C.copy()
+    Hm.data[-5] = 300.0                                  # only the LAST block falls back
+    np.testing.assert_array_equal(mu.atac.pp.tfidf(SimpleAnnData(Hm.copy()), inplace=False).data,
+                                  _device.tfidf_csr(mu.DeviceCSR.from_scipy(Hm)).get().data)
     # the result keeps its own index arrays when the source stays alive
     out = mu.atac.pp.tfidf(SimpleAnnData(C), inplace=False)
     assert out.indices is not C.indices and out.indptr is not C.indptr

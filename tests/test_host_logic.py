@@ -35,6 +35,22 @@ class ScipyOperator:
         return y.T @ y
 
 
+class SamplingOperator(ScipyOperator):
+    """ScipyOperator with the optional residual_sample hook (here on every 4th peak)."""
+
+    def __init__(self, A):
+        super().__init__(A)
+        self.samples = 0
+
+    def residual_sample(self, Uk, Vk, sig):
+        self.samples += 1
+        k = Vk.shape[1]
+        idx = np.arange(0, self.d, 4)
+        W = (self.At[idx] @ Uk.numpy())[:, :k]
+        R = W.astype(np.float64) - Vk.numpy()[idx].astype(np.float64) * sig.numpy()[None, :k]
+        return torch.from_numpy(np.sqrt((R * R).sum(0) * (self.d / idx.size)) / sig.numpy()[:k])
+
+
 def test_containers_view_copy_slots():
     x = np.arange(20, dtype=float).reshape(4, 5)
     ad = SimpleAnnData(x)
@@ -271,3 +287,32 @@ def test_reference_arm_does_not_load_the_cuda_library():
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert '"impl": "reference"' in out.stdout
+
+
+def test_sampled_residual_check_saves_the_confirming_pass():
+    """When the history predicts convergence the driver estimates the residual on a sample of the peaks and skips the
+    pass that would only confirm it; the result meets the same parity bar, an operator without the hook is unaffected,
+    and a failed estimate falls through to the full pass."""
+    k, P = 20, 32
+    X = tfidf_ref(generate_host(1500, 1200, 0.05, n_topics=12, seed=3)).astype(np.float32)
+    ref = lsi_ref(X, k + 1, dtype=np.float64)
+    s_next = ref["svalues"][k]
+    ref = {"svalues": ref["svalues"][:k], "U": ref["U"][:, :k], "LSI": ref["LSI"][:, :k]}
+    U0, s0, V0, info0 = truncated_svd(ScipyOperator(X), k, P, tol=1e-5, polish=False)
+    op = SamplingOperator(X)
+    U, s, V, info = truncated_svd(op, k, P, tol=1e-5, polish=False)
+    assert info0.sampled_checks == 0 and op.samples == info.sampled_checks >= 1
+    if info.sampled_stop:
+        assert info.passes == info0.passes - 1
+    out = compare_lsi({"svalues": s.numpy(), "U": U.numpy(), "LSI": V.numpy()}, ref, rtol=1e-4, s_next=s_next)
+    assert out["sigma_rel"] < 1e-5
+    assert np.abs(U.numpy().T.astype(np.float64) @ U.numpy() - np.eye(k)).max() < 1e-5
+
+    class Pessimist(SamplingOperator):
+        def residual_sample(self, Uk, Vk, sig):
+            return super().residual_sample(Uk, Vk, sig) * 1e3          # never accepted
+
+    op2 = Pessimist(X)
+    U2, s2, V2, info2 = truncated_svd(op2, k, P, tol=1e-5, polish=False)
+    assert not info2.sampled_stop and info2.passes == info0.passes and info2.converged
+    np.testing.assert_allclose(s2.numpy(), s0.numpy(), rtol=1e-6)
