@@ -238,7 +238,11 @@ def lsi_step_fn(ctx, A, k, tol):
     def step():
         ad = mu.SimpleAnnData(A, obs=obs0, var=var0)  # counts stay untouched: tfidf writes a new matrix
         mu.atac.pp.tfidf(ad)
-        return mu.atac.tl.lsi(ad, n_comps=k, tol=tol, return_info=True)
+        info = mu.atac.tl.lsi(ad, n_comps=k, tol=tol, return_info=True)
+        # leading singular values (stdev * sqrt(n-1), tools.py:65): the same global matrix must give the same
+        # values on any number of GPUs (strong leg at N ranks vs main leg at 1 rank)
+        info.sigma_head = [float(x) * float(np.sqrt(max(A.n_total - 1, 1))) for x in ad.uns["lsi"]["stdev"][:4]]
+        return info
     return step
 
 
@@ -384,6 +388,7 @@ def main():
         ms_s, kern_s, _, info_s, _ = timed_steps(ctx, lsi_step_fn(ctx, As, k, args.tol), args.steps, max(args.warmup, 1))
         note("strong", {"ms_per_step": ms_s / args.steps})
         strong = {"cells_total": ns * world, "cells_per_gpu": ns, "ms_per_step": ms_s / args.steps,
+                  "sigma_head": getattr(info_s, "sigma_head", None),
                   "value": ns * world * args.steps / (ms_s / 1e3), "unit": "cells/s", "passes": info_s.passes,
                   "spmm_ms_per_step": float(np.sum([np.sum(v) for n_, v in kern_s.items() if "spmm" in n_])) / args.steps}
         del As
@@ -508,6 +513,9 @@ def main():
                        "lsi": {"block": info.block, "iterations": info.iterations, "passes": info.passes,
                                "passes_half_operand": getattr(info, "lowp_passes", 0),
                                "tol": args.tol, "converged": info.converged, "stalled": info.stalled,
+                               "sigma_head": getattr(info, "sigma_head", None),
+                               "sampled_stop": getattr(info, "sampled_stop", False),
+                               "replica_repairs": getattr(info, "replica_repairs", 0),
                                "max_rel_residual": max(info.residuals),
                                "residual_history": [float("%.3g" % h) for h in info.history]}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -74,14 +74,17 @@ MUB_SIMD_CLONES static uint64_t hash_run_i64(const int64_t* src, size_t n, uint6
 // float32 -> uint8 for count data (peak counts are "mostly 1 and 2"): a quarter of the bytes on the bus.  Returns
 // non-zero if some value is not an integer in [0, 255] (the caller then sends the block as it is).
 MUB_SIMD_CLONES static int narrow_f32_u8(uint8_t* dst, const float* src, size_t n) {
+    // branch-free so that it vectorises (cvttps2dq / cvtdq2ps / compare / pack): a float that is not an integer in
+    // [0, 255] either fails the round trip or leaves bits above the low byte (NaN and out-of-range values convert to
+    // INT_MIN on x86)
     int bad = 0;
     for (size_t i = 0; i < n; ++i) {
         const float v = src[i];
-        const int iv = (v >= 0.f && v <= 255.f) ? (int)v : -1;
-        bad |= (iv < 0) | ((float)iv != v);
+        const int iv = (int)v;
+        bad |= ((float)iv != v) | (iv & ~255);
         dst[i] = (uint8_t)iv;
     }
-    return bad;
+    return bad != 0;
 }
 
 static uint64_t hash_only(const void* src, size_t n, int elem_bytes, uint64_t pos0) {
