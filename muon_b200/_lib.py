@@ -144,11 +144,20 @@ import contextlib
 import time as _time
 
 PHASES = None   # None, or dict name -> seconds
+NVTX = os.environ.get("MUON_B200_NVTX", "0") == "1"   # NVTX ranges around the phases (readable nsys timelines)
 
 
 @contextlib.contextmanager
 def phase(name: str):
     if PHASES is None:
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(name)
+            try:
+                yield
+            finally:
+                torch.cuda.nvtx.range_pop()
+            return
         yield
         return
     import torch
