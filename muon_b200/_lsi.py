@@ -96,7 +96,7 @@ class CsrOperator:
 
     def residual_sample(self, Uk, Vk, sig):
         """Estimate of the relative residuals ||A^T u_i - sigma_i v_i|| / sigma_i of k triplets from 1/16 of the
-        peaks (16 evenly spaced contiguous blocks of rows of A^T): ||r||^2 ~ (d/|S|) * sum_{j in S} r_j^2.  Costs 1/16
+        peaks (4 evenly spaced contiguous blocks of rows of A^T; peak indices carry no structure): ||r||^2 ~ (d/|S|) * sum_{j in S} r_j^2.  Costs 1/16
         of a pass; the driver uses it to skip the pass that would only confirm convergence."""
         blocks = self._dev.sample_row_blocks(self.d)
         with phase("lsi.residual_sample"):
