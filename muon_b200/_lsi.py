@@ -79,8 +79,8 @@ class CsrOperator:
             return self._dev.spmm(self.A, V, dynamic=False)
 
     def aty(self, Y, lowp: bool = False):
-        """A^T Y summed over the cell shards.  Multi-GPU: the product is computed in blocks of peaks and the
-        allreduce of block c runs (NCCL stream) under the SpMM of block c+1; only the last block's is exposed."""
+        """A^T Y summed over the cell shards.  Multi-GPU: with $MUON_B200_AR_CHUNKS > 1 the product is computed in
+        blocks of peaks and the allreduce of block c runs (NCCL stream) under the SpMM of block c+1."""
         self.passes += 1
         with phase("lsi.spmm_aty"):
             if not _dist.is_distributed():
@@ -92,7 +92,9 @@ class CsrOperator:
                 w.wait()
             return W
 
-    AR_CHUNKS = int(os.environ.get("MUON_B200_AR_CHUNKS", "4"))
+    # measured (profiles/README.md, multi-GPU): 4 blocks hide a ~0.3 ms allreduce but cost ~25 ms per step in smaller,
+    # less efficient SpMM launches, so the default is one block (the overlapped path stays available and tested)
+    AR_CHUNKS = int(os.environ.get("MUON_B200_AR_CHUNKS", "1"))
 
     def residual_sample(self, Uk, Vk, sig):
         """Estimate of the relative residuals ||A^T u_i - sigma_i v_i|| / sigma_i of k triplets from 1/16 of the
