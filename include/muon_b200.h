@@ -66,11 +66,13 @@ int mub_tfidf_reduce_f64(const int64_t* indptr, const int32_t* indices, const do
  * row_base = its absolute row number (a multiple of the tile height).  Optional by-product: col_count
  * [n_chunks x n_cols] int32 (zeroed by the caller, accumulated) = stored entries per (row chunk, column), row
  * chunks given by chunk_bounds[n_chunks+1] (absolute rows, multiples of the tile height): the histogram
- * mub_csr_transpose_count would otherwise compute in a pass of its own. */
+ * mub_csr_transpose_count would otherwise compute in a pass of its own.  Second optional by-product: rb_count
+ * uint16[ceil(n_rows_total / tile height)][n_cols] = stored entries per (row block, column), written (not accumulated)
+ * for the blocks of this call; mub_csr_transpose_fill_tiled turns it into write offsets. */
 int mub_tfidf_reduce_tiled_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
                                int32_t n_cols, float* row_sum, float* col_sum, int32_t* status, uint32_t flags,
                                int32_t* col_count, const int64_t* chunk_bounds, int32_t n_chunks, int64_t row_base,
-                               mub_stream_t stream);
+                               uint16_t* rb_count, mub_stream_t stream);
 int mub_tfidf_tile_rows(void);
 /* idf[j] = n_obs_total / col_sum[j], log1p if MUB_TFIDF_LOG_IDF (preproc.py:106-108) */
 int mub_tfidf_idf_f32(const float* col_sum, int32_t n_cols, double n_obs_total, uint32_t flags,
@@ -127,6 +129,13 @@ int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const 
 int mub_csr_transpose_fill_pairs(const int64_t* indptr, const int32_t* indices, const float* data,
                                  int64_t n_rows, int32_t n_cols, int64_t row_offset, const int64_t* t_indptr,
                                  int64_t* cursor, int32_t* t_pairs, mub_stream_t stream);
+/* fill_pairs without global atomics, for a row panel that starts on a row-block boundary: rb_count points at the
+ * panel's first row block (see mub_tfidf_reduce_tiled_f32), indptr at its first row, t_indptr[n_cols+1] are the panel's
+ * transposed row offsets, base is uint32 scratch [ceil(n_rows / tile height)][n_cols] (the scanned write offsets),
+ * status (int32, zeroed by the caller) gets bit0 if counts and t_indptr disagree (then the result is invalid). */
+int mub_csr_transpose_fill_tiled(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                                 int32_t n_cols, const uint16_t* rb_count, const int64_t* t_indptr, uint32_t* base,
+                                 int32_t* t_pairs, int32_t* status, mub_stream_t stream);
 int mub_spmm_csrp_f32(const int64_t* indptr, const int32_t* pairs, int64_t n_rows, int64_t n_cols,
                       const float* B, int32_t ld, float* C, int32_t accumulate, unsigned long long* row_counter,
                       mub_stream_t stream);

@@ -11,6 +11,6 @@ hand-written CUDA kernels behind the C ABI in include/muon_b200.h.  There is no 
 """
 from . import atac, pp, tl  # noqa: F401
 from ._containers import SimpleAnnData, SimpleMuData  # noqa: F401
-from ._device import DeviceCSR  # noqa: F401
+from ._device import DeviceCSR, release_all_resident, release_resident, trim_host_cache  # noqa: F401
 
 __version__ = "0.1.0"

@@ -434,8 +434,9 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
         bounds = chunk_bounds(n)
         counts = torch.zeros((N_CHUNKS, d), dtype=torch.int32, device=dev)
         cb = torch.tensor(bounds, dtype=torch.int64, device=dev)
+        rb_counts = torch.empty((-(-n // tile_rows()), d), dtype=torch.int16, device=dev)      # uint16 entries per (512-row block, column)
         call("mub_tfidf_reduce_tiled_f32", ptr(A.indptr), ptr(A.indices), ptr(A.data), n, d, ptr(row_sum), ptr(col_sum),
-             ptr(st_t), flags, ptr(counts), ptr(cb), N_CHUNKS, 0, st)
+             ptr(st_t), flags, ptr(counts), ptr(cb), N_CHUNKS, 0, ptr(rb_counts), st)
         bad = int(st_t[0])
         if check_canonical and bad != 0:
             return None  # caller canonicalises (duplicates / explicit zeros / unsorted rows) and retries
@@ -458,11 +459,13 @@ def tfidf_csr(A: DeviceCSR, log_tf=True, log_idf=True, log_tfidf=False, scale_fa
     res._aux = {"row_sum": row_sum, "col_sum": col_sum, "idf": idf}
     if counts is not None:
         res._aux["col_counts"] = (bounds, counts)
+        res._aux["rb_counts"] = rb_counts
     return res
 
 
 def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None, k0: Optional[int] = None,
-                  k1: Optional[int] = None, pairs: bool = False, col_count: Optional[torch.Tensor] = None):
+                  k1: Optional[int] = None, pairs: bool = False, col_count: Optional[torch.Tensor] = None,
+                  rb_counts: Optional[torch.Tensor] = None, scratch: Optional[dict] = None):
     """Build the CSR of (A[row0:row1])^T on the device (count -> scan -> atomic-cursor fill).
     Row indices stored in the result are local to the panel (0 .. row1-row0).  ``k0``/``k1`` are the
     non-zero offsets of the row range if the caller already knows them (avoids a host sync)."""
@@ -485,6 +488,18 @@ def csr_transpose(A: DeviceCSR, row0: int = 0, row1: Optional[int] = None, k0: O
         call("mub_csr_transpose_count", ptr(A.indices) + 4 * k0, nnz, d, ptr(t_count), st)
     t_indptr = torch.cumsum(t_count, 0)
     cursor = torch.empty(max(d, 1), dtype=torch.int64, device=dev)
+    if pairs and rb_counts is not None and col_count is not None and row0 % tile_rows() == 0:
+        # atomic-free fill: write offsets of every 512-row block from the scanned per-block counts (transpose.cu)
+        t_pairs = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
+        nb = -(-(row1 - row0) // tile_rows())
+        if scratch.get("base") is None or scratch["base"].numel() < nb * d:
+            scratch["base"] = torch.empty(nb * d, dtype=torch.int32, device=dev)
+        if scratch.get("status") is None:
+            scratch["status"] = torch.zeros(1, dtype=torch.int32, device=dev)
+        call("mub_csr_transpose_fill_tiled", ptr(A.indptr) + 8 * row0, ptr(A.indices), ptr(A.data), row1 - row0, d,
+             ptr(rb_counts) + 2 * (row0 // tile_rows()) * d, ptr(t_indptr), ptr(scratch["base"]), ptr(t_pairs),
+             ptr(scratch["status"]), st)
+        return DevicePairs(t_indptr, t_pairs, (d, row1 - row0))
     if pairs:
         t_pairs = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
         call("mub_csr_transpose_fill_pairs", ptr(A.indptr) + 8 * row0, ptr(A.indices), ptr(A.data), row1 - row0, d, 0,
@@ -511,7 +526,7 @@ class TransposedPanels:
         n = A.shape[0]
         rows = max(1, self.L2_BUDGET // (4 * pad))
         n_panels = max(1, -(-n // rows))
-        counts = None
+        counts, rb = None, None
         if n_panels <= N_CHUNKS:
             # 1, 2, 4, 8 or 16 panels, each a union of consecutive row chunks (see chunk_bounds): the entry counts
             # per (chunk, column) left behind by the TF-IDF reduce pass then replace the counting pass
@@ -523,9 +538,12 @@ class TransposedPanels:
             if "col_counts" in aux and list(aux["col_counts"][0]) == cb:
                 cc = aux["col_counts"][1]
                 counts = [cc[i * per:(i + 1) * per].sum(0, dtype=torch.int64) for i in range(n_panels)]
+                if os.environ.get("MUON_B200_FILL_TILED", "1") != "0" and not side_stream:
+                    rb = aux.get("rb_counts")
         else:
             bounds = [round(i * n / n_panels) for i in range(n_panels + 1)]
         self.counts_reused = counts is not None
+        self.tiled_fill = False
         self.shape = (A.shape[1], n)
         # non-zero offsets of the panel boundaries: one small D2H up front, no host syncs afterwards
         ks = A.indptr[torch.tensor(bounds, device=A.indptr.device)].tolist()
@@ -545,9 +563,17 @@ class TransposedPanels:
                 for t in (T.indptr, T.pairs):
                     t.record_stream(main)
         else:
-            self.panels = [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True,
-                                                                    col_count=counts[i] if counts else None))
-                           for i in range(n_panels) if bounds[i + 1] > bounds[i]]
+            scratch = {}
+            build = lambda rbc: [(bounds[i], bounds[i + 1], csr_transpose(A, bounds[i], bounds[i + 1], ks[i], ks[i + 1], pairs=True,  # noqa: E731
+                                                                          col_count=counts[i] if counts else None, rb_counts=rbc,
+                                                                          scratch=scratch))
+                                 for i in range(n_panels) if bounds[i + 1] > bounds[i]]
+            self.panels = build(rb)
+            if rb is not None:
+                if int(scratch["status"][0]) == 0:
+                    self.tiled_fill = True
+                else:          # counts and pattern disagree (the matrix was modified after tfidf): atomic-cursor fill
+                    self.panels = build(None)
 
     def wait(self):
         if self.ready is not None:
@@ -604,7 +630,7 @@ def _row_range(rows, n):
     return rows
 
 
-def sample_row_blocks(d: int, fraction: int = 16, n_blocks: int = 16):
+def sample_row_blocks(d: int, fraction: int = 16, n_blocks: int = 4):
     """``n_blocks`` evenly spaced contiguous row blocks covering 1/``fraction`` of d rows -> list of (j0, j1)."""
     bs = max(1, d // (fraction * n_blocks))
     out, last = [], 0
@@ -753,6 +779,7 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     bounds = chunk_bounds(n) if tiled else None
     counts = torch.zeros((N_CHUNKS, d), dtype=torch.int32, device=dev) if tiled else None
     cb = torch.tensor(bounds, dtype=torch.int64, device=dev) if tiled else None
+    rb_counts = torch.empty((-(-n // tile_rows()), d), dtype=torch.int16, device=dev) if tiled else None
     side.wait_stream(main)                      # allocations above are ordered on the main stream
     narrow = indices_h.dtype == np.int64
     assert narrow or indices_h.dtype == np.int32, indices_h.dtype
@@ -773,7 +800,7 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
         main.wait_event(side.record_event())
         if tiled:      # host matrices must be canonical anyway (checked here): sorted rows, so the tiled pass applies
             call("mub_tfidf_reduce_tiled_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,
-                 ptr(col_sum), ptr(status), flags, ptr(counts), ptr(cb), N_CHUNKS, r0, main.cuda_stream)
+                 ptr(col_sum), ptr(status), flags, ptr(counts), ptr(cb), N_CHUNKS, r0, ptr(rb_counts), main.cuda_stream)
         else:
             call("mub_tfidf_reduce_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), r1 - r0, d, ptr(row_sum) + 4 * r0,
                  ptr(col_sum), ptr(status), flags, main.cuda_stream)
@@ -813,6 +840,7 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     res._aux = {"row_sum": row_sum, "col_sum": col_sum, "idf": idf}
     if tiled:
         res._aux["col_counts"] = (bounds, counts)
+        res._aux["rb_counts"] = rb_counts
     fps = {"blocks": [(k0, k1) for (_, _, k0, k1) in blocks], "indices": fp_idx, "data": fp_out,
            "indptr": host_pool().fingerprint(indptr_h.astype(np.int64, copy=False).view(np.uint32)) if n else 0}
     return res, out_h, fps

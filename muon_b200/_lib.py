@@ -26,7 +26,8 @@ SIGNATURES = {
     "mub_device_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(i64)],
     "mub_tfidf_reduce_f32": [vp, vp, vp, i64, i32, vp, vp, vp, u32, vp],
     "mub_tfidf_reduce_f64": [vp, vp, vp, i64, i32, vp, vp, vp, u32, vp],
-    "mub_tfidf_reduce_tiled_f32": [vp, vp, vp, i64, i32, vp, vp, vp, u32, vp, vp, i32, i64, vp],
+    "mub_tfidf_reduce_tiled_f32": [vp, vp, vp, i64, i32, vp, vp, vp, u32, vp, vp, i32, i64, vp, vp],
+    "mub_csr_transpose_fill_tiled": [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp],
     "mub_tfidf_tile_rows": [],
     "mub_tfidf_idf_f32": [vp, i32, f64, u32, vp, vp],
     "mub_tfidf_idf_f64": [vp, i32, f64, u32, vp, vp],
@@ -104,7 +105,7 @@ def load():
 
 
 # kernels launched per successful call (for the benchmark's gpu_launches claim)
-KERNELS_PER_CALL = {"mub_csr_transpose_fill": 2, "mub_csr_transpose_fill_pairs": 2, "mub_gram_f32": 2, "mub_version": 0, "mub_device_info": 0,
+KERNELS_PER_CALL = {"mub_csr_transpose_fill_tiled": 2, "mub_csr_transpose_fill": 2, "mub_csr_transpose_fill_pairs": 2, "mub_gram_f32": 2, "mub_version": 0, "mub_device_info": 0,
                     "mub_tfidf_tile_rows": 0, "mub_stager_create": 0, "mub_stager_destroy": 0, "mub_stager_h2d": 0, "mub_stager_d2h": 0, "mub_host_fingerprint": 0}
 LAUNCHES = 0          # running count of kernels launched through this binding
 PROFILE = None        # None, or dict name -> list[(start_event, end_event)] filled by call()
@@ -144,11 +145,20 @@ import contextlib
 import time as _time
 
 PHASES = None   # None, or dict name -> seconds
+NVTX = os.environ.get("MUON_B200_NVTX", "0") == "1"   # NVTX ranges around the phases (readable nsys timelines)
 
 
 @contextlib.contextmanager
 def phase(name: str):
     if PHASES is None:
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(name)
+            try:
+                yield
+            finally:
+                torch.cuda.nvtx.range_pop()
+            return
         yield
         return
     import torch

@@ -79,8 +79,8 @@ class CsrOperator:
             return self._dev.spmm(self.A, V, dynamic=False)
 
     def aty(self, Y, lowp: bool = False):
-        """A^T Y summed over the cell shards.  Multi-GPU: the product is computed in blocks of peaks and the
-        allreduce of block c runs (NCCL stream) under the SpMM of block c+1; only the last block's is exposed."""
+        """A^T Y summed over the cell shards.  Multi-GPU: with $MUON_B200_AR_CHUNKS > 1 the product is computed in
+        blocks of peaks and the allreduce of block c runs (NCCL stream) under the SpMM of block c+1."""
         self.passes += 1
         with phase("lsi.spmm_aty"):
             if not _dist.is_distributed():
@@ -92,11 +92,13 @@ class CsrOperator:
                 w.wait()
             return W
 
-    AR_CHUNKS = int(os.environ.get("MUON_B200_AR_CHUNKS", "4"))
+    # measured (profiles/README.md, multi-GPU): 4 blocks hide a ~0.3 ms allreduce but cost ~25 ms per step in smaller,
+    # less efficient SpMM launches, so the default is one block (the overlapped path stays available and tested)
+    AR_CHUNKS = int(os.environ.get("MUON_B200_AR_CHUNKS", "1"))
 
     def residual_sample(self, Uk, Vk, sig):
         """Estimate of the relative residuals ||A^T u_i - sigma_i v_i|| / sigma_i of k triplets from 1/16 of the
-        peaks (16 evenly spaced contiguous blocks of rows of A^T): ||r||^2 ~ (d/|S|) * sum_{j in S} r_j^2.  Costs 1/16
+        peaks (4 evenly spaced contiguous blocks of rows of A^T; peak indices carry no structure): ||r||^2 ~ (d/|S|) * sum_{j in S} r_j^2.  Costs 1/16
         of a pass; the driver uses it to skip the pass that would only confirm convergence."""
         blocks = self._dev.sample_row_blocks(self.d)
         with phase("lsi.residual_sample"):

@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(kTileThreads, 2)
 tfidf_reduce_tiled_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                           const float* __restrict__ data, int64_t n_rows, int32_t n_cols, float* __restrict__ row_sum,
                           float* __restrict__ col_sum, int* __restrict__ status, int32_t* __restrict__ col_count,
-                          const int64_t* __restrict__ chunk_bounds, int32_t n_chunks, int64_t row_base) {
+                          const int64_t* __restrict__ chunk_bounds, int32_t n_chunks, int64_t row_base,
+                          uint16_t* __restrict__ rb_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sums = reinterpret_cast<float*>(smem_raw);
     unsigned* cnts = reinterpret_cast<unsigned*>(smem_raw + sizeof(float) * kTileCols);
@@ -192,6 +193,9 @@ tfidf_reduce_tiled_kernel(const int64_t* __restrict__ indptr, const int32_t* __r
                 atomicAdd(col_sum + c_lo + j, sums[j]);
                 if (col_count != nullptr) atomicAdd(col_count + (size_t)chunk * n_cols + c_lo + j, (int)cn);
             }
+            // entries of this ROW BLOCK per column (<= kTileRows, fits 16 bits): the tiled transposition derives
+            // every block's write offsets from these, so it needs no global atomics (transpose.cu)
+            if (rb_count != nullptr) rb_count[((size_t)(row_base / kTileRows) + blockIdx.x) * n_cols + c_lo + j] = (uint16_t)cn;
         }
         __syncthreads();
     }
@@ -317,7 +321,7 @@ extern "C" {
 int mub_tfidf_reduce_tiled_f32(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
                                int32_t n_cols, float* row_sum, float* col_sum, int32_t* status, uint32_t flags,
                                int32_t* col_count, const int64_t* chunk_bounds, int32_t n_chunks, int64_t row_base,
-                               mub_stream_t stream) {
+                               uint16_t* rb_count, mub_stream_t stream) {
     MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "tfidf_reduce_tiled: negative shape");
     if (n_rows == 0) return 0;
     MUB_REQUIRE(indptr && row_sum && col_sum && status, "tfidf_reduce_tiled: null pointer (status is mandatory: it reports rows "
@@ -331,11 +335,11 @@ int mub_tfidf_reduce_tiled_f32(const int64_t* indptr, const int32_t* indices, co
     if (flags & MUB_TFIDF_BINARIZE) {
         cudaFuncSetAttribute(mub::tfidf_reduce_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         mub::tfidf_reduce_tiled_kernel<true><<<(int)grid, mub::kTileThreads, smem, s>>>(
-            indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, col_count, chunk_bounds, n_chunks, row_base);
+            indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, col_count, chunk_bounds, n_chunks, row_base, rb_count);
     } else {
         cudaFuncSetAttribute(mub::tfidf_reduce_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         mub::tfidf_reduce_tiled_kernel<false><<<(int)grid, mub::kTileThreads, smem, s>>>(
-            indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, col_count, chunk_bounds, n_chunks, row_base);
+            indptr, indices, data, n_rows, n_cols, row_sum, col_sum, status, col_count, chunk_bounds, n_chunks, row_base, rb_count);
     }
     return mub::check_launch("tfidf_reduce_tiled");
 }

@@ -103,6 +103,87 @@ transpose_fill_pairs_kernel(const int64_t* __restrict__ indptr, const int32_t* _
     }
 }
 
+// ---- tiled fill: no global atomics ------------------------------------------------------------------------
+// The atomic-cursor fill above spends one global ATOM (with return) plus one scattered 8-byte store per non-zero
+// and is bound by that queue (ncu: lg_throttle 289, issue-active 2 %).  When the TF-IDF reduce pass has left the
+// entry count of every (512-row block, column) behind (tfidf.cu, rb_count), the write offset of block b in
+// column c is  t_indptr[c] + sum of the counts of the panel's earlier blocks  -- a column-wise scan -- and a CTA
+// that owns block b only has to hand out consecutive slots INSIDE its own range: per-column cursors in shared
+// memory, tile by tile over the columns, exactly the sweep of tfidf_reduce_tiled_kernel.
+constexpr int kFillTileCols = 12288;   // 48 KB of cursors
+constexpr int kFillRows = 512;         // must equal the reduce kernel's block height (mub_tfidf_tile_rows)
+constexpr int kFillThreads = 512;
+
+// base[b][c] = t_indptr[c] + sum_{b' < b} count[b'][c] for the blocks of one panel (one thread per column)
+__global__ void __launch_bounds__(256)
+transpose_scan_blocks_kernel(const uint16_t* __restrict__ rb_count, int32_t n_cols, int64_t n_blocks,
+                             const int64_t* __restrict__ t_indptr, uint32_t* __restrict__ base, int* __restrict__ status) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cols) return;
+    unsigned long long run = (unsigned long long)t_indptr[c];
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        base[(size_t)b * n_cols + c] = (uint32_t)run;
+        run += rb_count[(size_t)b * n_cols + c];
+    }
+    if (run != (unsigned long long)t_indptr[c + 1] || run > 0xffffffffull) atomicOr(status, 1);   // counts and indptr disagree
+}
+
+__global__ void __launch_bounds__(kFillThreads, 2)
+transpose_fill_tiled_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            const float* __restrict__ data, int64_t n_rows, int32_t n_cols,
+                            const uint32_t* __restrict__ base, int2* __restrict__ t_pairs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* cursor = reinterpret_cast<unsigned*>(smem_raw);
+    int* cur = reinterpret_cast<int*>(smem_raw + sizeof(unsigned) * kFillTileCols);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kFillThreads / 32;
+    const int64_t r0 = (int64_t)blockIdx.x * kFillRows;
+    const int rows_here = (int)((n_rows - r0) < kFillRows ? (n_rows - r0) : kFillRows);
+    for (int r = threadIdx.x; r < kFillRows; r += kFillThreads) cur[r] = 0;
+    const uint32_t* my_base = base + (size_t)blockIdx.x * n_cols;
+    const int n_tiles = (n_cols + kFillTileCols - 1) / kFillTileCols;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int c_lo = t * kFillTileCols;
+        const int c_hi = (c_lo + kFillTileCols < n_cols) ? c_lo + kFillTileCols : n_cols;
+        for (int j = threadIdx.x; j < c_hi - c_lo; j += kFillThreads) cursor[j] = my_base[c_lo + j];
+        __syncthreads();
+        for (int r = warp; r < rows_here; r += kWarps) {
+            const int64_t s0 = __ldg(indptr + r0 + r), e = __ldg(indptr + r0 + r + 1);
+            int64_t k = s0 + cur[r];
+            const int row_local = (int)(r0 + r);
+            for (;;) {
+                const int64_t k0 = k + lane, k1 = k0 + 32, k2 = k0 + 64;
+                const int c0 = k0 < e ? ld_stream(indices + k0) : 0x7fffffff;
+                const int c1 = k1 < e ? ld_stream(indices + k1) : 0x7fffffff;
+                const int c2 = k2 < e ? ld_stream(indices + k2) : 0x7fffffff;
+                const float v0 = k0 < e ? ld_stream(data + k0) : 0.f;
+                const float v1 = k1 < e ? ld_stream(data + k1) : 0.f;
+                const float v2 = k2 < e ? ld_stream(data + k2) : 0.f;
+                int taken = 0;
+                bool stop = false;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int c = u == 0 ? c0 : (u == 1 ? c1 : c2);
+                    const float v = u == 0 ? v0 : (u == 1 ? v1 : v2);
+                    const bool in = !stop && c < c_hi;
+                    const int n_in = __popc(__ballot_sync(0xffffffffu, in));
+                    if (in && c >= c_lo) {
+                        const unsigned slot = atomicAdd(&cursor[c - c_lo], 1u);
+                        t_pairs[slot] = make_int2(row_local, __float_as_int(v));
+                    }
+                    taken += n_in;
+                    if (n_in < 32) stop = true;
+                }
+                k += taken;
+                if (stop || k >= e) break;
+            }
+            __syncwarp();
+            if (lane == 0) cur[r] = (int)(k - s0);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256)
 row_stats_pairs_kernel(const int64_t* __restrict__ indptr, const int2* __restrict__ pairs, int64_t n_rows,
                        double* __restrict__ sum, double* __restrict__ sumsq) {
@@ -231,3 +312,22 @@ int mub_csr_transpose_fill(const int64_t* indptr, const int32_t* indices, const 
 }
 
 }  // extern "C"
+
+// ---- tiled fill (needs the per-row-block counts of mub_tfidf_reduce_tiled_f32) ------------------------------------
+extern "C" int mub_csr_transpose_fill_tiled(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_rows,
+                                            int32_t n_cols, const uint16_t* rb_count, const int64_t* t_indptr, uint32_t* base,
+                                            int32_t* t_pairs, int32_t* status, mub_stream_t stream) {
+    MUB_REQUIRE(n_rows >= 0 && n_cols >= 0, "transpose_fill_tiled: negative shape");
+    if (n_rows == 0 || n_cols == 0) return 0;
+    MUB_REQUIRE(indptr && rb_count && t_indptr && base && t_pairs && status, "transpose_fill_tiled: null pointer");
+    MUB_REQUIRE(((uintptr_t)t_pairs & 7) == 0, "transpose_fill_tiled: t_pairs must be 8-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n_blocks = (n_rows + mub::kFillRows - 1) / mub::kFillRows;
+    MUB_REQUIRE(n_blocks < (1ll << 31), "transpose_fill_tiled: too many rows");
+    mub::transpose_scan_blocks_kernel<<<(n_cols + 255) / 256, 256, 0, s>>>(rb_count, n_cols, n_blocks, t_indptr, base, status);
+    const size_t smem = sizeof(unsigned) * mub::kFillTileCols + sizeof(int) * mub::kFillRows;
+    cudaFuncSetAttribute(mub::transpose_fill_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mub::transpose_fill_tiled_kernel<<<(int)n_blocks, mub::kFillThreads, smem, s>>>(indptr, indices, data, n_rows, n_cols, base,
+                                                                                  (int2*)t_pairs);
+    return mub::check_launch("transpose_fill_tiled");
+}

@@ -281,7 +281,21 @@ def test_tiled_reduce_equals_atomic_reduce_and_counts_feed_the_transposition(cud
     monkeypatch.setattr(_device.TransposedPanels, "L2_BUDGET", 1 << 18)       # 1024 cells per panel at pad 64 -> 8 panels
     Tp = _device.TransposedPanels(got, 64)
     Tq = _device.TransposedPanels(ref, 64)
-    assert Tp.counts_reused and not Tq.counts_reused and len(Tp.panels) == len(Tq.panels) >= 4
+    assert Tp.counts_reused and Tp.tiled_fill and not Tq.counts_reused and not Tq.tiled_fill
+    assert len(Tp.panels) == len(Tq.panels) >= 4
+    monkeypatch.setenv("MUON_B200_FILL_TILED", "0")
+    Tr = _device.TransposedPanels(got, 64)                       # reused counts, atomic-cursor fill
+    assert Tr.counts_reused and not Tr.tiled_fill
+    monkeypatch.setenv("MUON_B200_FILL_TILED", "1")
+    for (a0, a1, Ta), (b0, b1, Tb) in zip(Tp.panels, Tr.panels):
+        # same ENTRIES per transposed row ((peak, cell) is unique): order by (peak, cell) and compare cells and value bits
+        assert torch.equal(Ta.indptr, Tb.indptr)
+        rows = torch.repeat_interleave(torch.arange(d, device=cuda), Ta.indptr[1:] - Ta.indptr[:-1])
+        ka = rows * (1 << 20) + Ta.pairs[:, 0].to(torch.int64)
+        kb = rows * (1 << 20) + Tb.pairs[:, 0].to(torch.int64)
+        oa, ob = torch.argsort(ka), torch.argsort(kb)
+        assert torch.equal(ka[oa], kb[ob]) and torch.equal(Ta.pairs[oa, 1], Tb.pairs[ob, 1])
+        assert int(Ta.pairs[:, 0].min()) >= 0 and int(Ta.pairs[:, 0].max()) < a1 - a0
     for (a0, a1, Ta), (b0, b1, Tb) in zip(Tp.panels, Tq.panels):
         assert (a0, a1) == (b0, b1) and torch.equal(Ta.indptr, Tb.indptr)
         Y = torch.randn((a1 - a0, 64), device=cuda)
