@@ -538,7 +538,10 @@ class TransposedPanels:
             if "col_counts" in aux and list(aux["col_counts"][0]) == cb:
                 cc = aux["col_counts"][1]
                 counts = [cc[i * per:(i + 1) * per].sum(0, dtype=torch.int64) for i in range(n_panels)]
-                if os.environ.get("MUON_B200_FILL_TILED", "1") != "0" and not side_stream:
+                # opt-in: the atomic-free tiled fill is correct but SLOWER at configs[1] (180 ms against 105 ms:
+                # each (row block, column) writes a ~120-byte run at its own time, so L2 merges less than under the
+                # row-ordered atomic-cursor fill) -- profiles/README.md, negative results
+                if os.environ.get("MUON_B200_FILL_TILED", "0") == "1" and not side_stream:
                     rb = aux.get("rb_counts")
         else:
             bounds = [round(i * n / n_panels) for i in range(n_panels + 1)]
