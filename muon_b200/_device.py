@@ -538,7 +538,10 @@ class TransposedPanels:
             if "col_counts" in aux and list(aux["col_counts"][0]) == cb:
                 cc = aux["col_counts"][1]
                 counts = [cc[i * per:(i + 1) * per].sum(0, dtype=torch.int64) for i in range(n_panels)]
-                if os.environ.get("MUON_B200_FILL_TILED", "1") != "0" and not side_stream:
+                # opt-in: the atomic-free tiled fill is correct but SLOWER at configs[1] (180 ms against 105 ms:
+                # each (row block, column) writes a ~120-byte run at its own time, so L2 merges less than under the
+                # row-ordered atomic-cursor fill) -- profiles/README.md, negative results
+                if os.environ.get("MUON_B200_FILL_TILED", "0") == "1" and not side_stream:
                     rb = aux.get("rb_counts")
         else:
             bounds = [round(i * n / n_panels) for i in range(n_panels + 1)]
@@ -818,18 +821,13 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     with _timed("alloc_out_s"):
         out_h = _ARENA.empty(nnz, np.float32)
 
-    def apply(b):
-        r0, r1, k0, k1 = blocks[b]
-        call("mub_tfidf_apply_f32", ptr(indptr) + 8 * r0, ptr(indices), ptr(data), ptr(data), r1 - r0, d,
-             ptr(row_sum) + 4 * r0, ptr(idf), float(scale_factor), flags, main.cuda_stream)
-        return main.record_event()
-
-    ev = apply(0) if blocks else None
-    for b, (r0, r1, k0, k1) in enumerate(blocks):
-        ev_next = apply(b + 1) if b + 1 < len(blocks) else None
-        side.wait_event(ev)
-        st.d2h(data[k0:k1], out_h[k0:k1], stream=side)
-        ev = ev_next
+    # apply over all rows (20 ms at configs[1]), then ONE download call: every d2h call drains its pipeline before it
+    # returns, so downloading block by block (to overlap the apply kernels) cost more in bubbles than it hid
+    if blocks:
+        call("mub_tfidf_apply_f32", ptr(indptr), ptr(indices), ptr(data), ptr(data), n, d, ptr(row_sum), ptr(idf),
+             float(scale_factor), flags, main.cuda_stream)
+        side.wait_event(main.record_event())
+        st.d2h(data, out_h, stream=side)
     main.wait_stream(side)
     # fingerprints of what crossed the bus, taken on the device copies (HBM-bound: ~10 ms per 24 GB) instead of
     # inside the host-side staging loops

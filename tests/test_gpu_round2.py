@@ -279,6 +279,7 @@ def test_tiled_reduce_equals_atomic_reduce_and_counts_feed_the_transposition(cud
         assert np.array_equal(counts[c].cpu().numpy(), want), c
     # transposed panels from the reused counts == panels from the counting pass (same indptr; same entry SETS per row)
     monkeypatch.setattr(_device.TransposedPanels, "L2_BUDGET", 1 << 18)       # 1024 cells per panel at pad 64 -> 8 panels
+    monkeypatch.setenv("MUON_B200_FILL_TILED", "1")             # the atomic-free fill (opt-in: measured slower at scale)
     Tp = _device.TransposedPanels(got, 64)
     Tq = _device.TransposedPanels(ref, 64)
     assert Tp.counts_reused and Tp.tiled_fill and not Tq.counts_reused and not Tq.tiled_fill
@@ -286,7 +287,6 @@ def test_tiled_reduce_equals_atomic_reduce_and_counts_feed_the_transposition(cud
     monkeypatch.setenv("MUON_B200_FILL_TILED", "0")
     Tr = _device.TransposedPanels(got, 64)                       # reused counts, atomic-cursor fill
     assert Tr.counts_reused and not Tr.tiled_fill
-    monkeypatch.setenv("MUON_B200_FILL_TILED", "1")
     for (a0, a1, Ta), (b0, b1, Tb) in zip(Tp.panels, Tr.panels):
         # same ENTRIES per transposed row ((peak, cell) is unique): order by (peak, cell) and compare cells and value bits
         assert torch.equal(Ta.indptr, Tb.indptr)
@@ -328,5 +328,5 @@ def test_tiled_reduce_equals_atomic_reduce_and_counts_feed_the_transposition(cud
     Ao = mu.DeviceCSR.from_scipy(Xo)
     rs, cs = torch.empty(n, device=cuda), torch.zeros(d, device=cuda)
     call("mub_tfidf_reduce_tiled_f32", ptr(Ao.indptr), ptr(Ao.indices), ptr(Ao.data), n, d, ptr(rs), ptr(cs), ptr(st), 0,
-         None, None, 0, 0, stream_ptr())
+         None, None, 0, 0, None, stream_ptr())
     assert int(st[0]) & 1
