@@ -12,7 +12,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmuon_b200.so")
+LIB_PATH = os.environ.get("MUON_B200_LIB") or os.path.join(_HERE, "csrc", "libmuon_b200.so")   # override: A/B builds
 
 _lock = threading.Lock()
 _lib = None
