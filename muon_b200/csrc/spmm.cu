@@ -119,7 +119,7 @@ __device__ __forceinline__ void spmm_row(const int32_t* __restrict__ indices, co
 }
 
 template <int P, bool PAIRS>
-__global__ void __launch_bounds__(kSpmmThreads)
+__global__ void __launch_bounds__(kSpmmThreads, (P <= 32 ? 4 : 2))
 spmm_csr_rowwarp_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                         const float* __restrict__ data, int64_t n_rows, const float* __restrict__ B,
                         float* __restrict__ C, int accumulate, unsigned long long* row_counter) {
