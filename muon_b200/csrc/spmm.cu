@@ -237,10 +237,10 @@ __device__ __forceinline__ void spmm_row_h(const int32_t* __restrict__ indices, 
     }
 }
 
-// 4 CTAs of 256 threads per SM (<= 64 registers): after the packed FMAs neither the issue slots (51 %) nor L2 (67 %)
-// are saturated at 3 CTAs/SM (76 registers, 32 % warps active) -- the kernel is latency-bound, so occupancy pays
+// (forcing 4 CTAs/SM -- 64 registers instead of 76 -- was measured: 52.3 ms per pass against 51.7, the spills cost what
+// the occupancy gains; profiles/README.md)
 template <int P, bool PAIRS>
-__global__ void __launch_bounds__(kSpmmThreads, (P <= 64 ? 4 : 2))
+__global__ void __launch_bounds__(kSpmmThreads)
 spmm_csr_rowwarp_h_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                           const float* __restrict__ data, int64_t n_rows, const __half* __restrict__ B,
                           float* __restrict__ C, int accumulate, float out_scale, unsigned long long* row_counter) {
