@@ -324,6 +324,17 @@ class DeviceCSR:
         return cls(to_device(X.indptr, device, np.int64), to_device(X.indices, device, np.int32),
                    to_device(data, device, dtype), X.shape)
 
+    @classmethod
+    def from_scipy_shard(cls, X, world: Optional[int] = None, rank: Optional[int] = None, device=None) -> "DeviceCSR":
+        """Upload this rank's row block of a host CSR that every rank can see (e.g. memory-mapped), the blocks cut so
+        that all ranks hold about the same number of stored entries (``_dist.balanced_row_range``).  The result
+        carries ``row0`` / ``n_total`` like the shards of the synthetic generator."""
+        r0, r1 = _dist.balanced_row_range(X.indptr, world, rank)
+        sub = X[r0:r1]
+        out = cls.from_scipy(sub, device=device)
+        out.row0, out._n_total = int(r0), int(X.shape[0])
+        return out
+
     def get(self, indptr_host=None, indices_host=None):
         """Download as scipy.sparse.csr_matrix.  Host index arrays may be passed to be reused
         (the sparsity pattern is never modified on the device)."""

@@ -53,3 +53,19 @@ def broadcast_(t: torch.Tensor, src: int = 0) -> torch.Tensor:
     if is_distributed():
         torch.distributed.broadcast(t, src=src)
     return t
+
+
+def balanced_row_range(indptr, world: int = None, rank_: int = None):
+    """Contiguous row block [r0, r1) of rank ``rank_`` of ``world`` such that every rank holds about the same number of
+    stored entries ("row blocks balanced by nnz, not by row count"; cells differ in depth).
+    ``indptr``: CSR row pointer of the WHOLE matrix (numpy array or tensor).  Defaults: the current process group."""
+    import numpy as np
+    world = world_size() if world is None else int(world)
+    rank_ = rank() if rank_ is None else int(rank_)
+    ip = indptr.cpu().numpy() if isinstance(indptr, torch.Tensor) else np.asarray(indptr)
+    n = ip.shape[0] - 1
+    nnz = int(ip[-1]) - int(ip[0])
+    cuts = [0] + [int(np.searchsorted(ip, int(ip[0]) + (nnz * i) // world, side="left")) for i in range(1, world)] + [n]
+    for i in range(1, len(cuts)):
+        cuts[i] = min(n, max(cuts[i], cuts[i - 1]))
+    return cuts[rank_], cuts[rank_ + 1]

@@ -316,3 +316,20 @@ def test_sampled_residual_check_saves_the_confirming_pass():
     U2, s2, V2, info2 = truncated_svd(op2, k, P, tol=1e-5, polish=False)
     assert not info2.sampled_stop and info2.passes == info0.passes and info2.converged
     np.testing.assert_allclose(s2.numpy(), s0.numpy(), rtol=1e-6)
+
+
+def test_nnz_balanced_row_blocks():
+    """Cell shards for multi-GPU runs are cut by stored entries, not by rows: contiguous, covering, and
+    within one row's worth of the ideal share even for very skewed depths."""
+    from muon_b200._dist import balanced_row_range
+    rng = np.random.default_rng(0)
+    lens = np.concatenate([rng.integers(1, 20, 5000), rng.integers(2000, 9000, 300), rng.integers(1, 20, 3000)])
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        blocks = [balanced_row_range(indptr, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == len(lens)
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        share = indptr[-1] / world
+        for r0, r1 in blocks:
+            assert abs((indptr[r1] - indptr[r0]) - share) <= lens.max() + 1
+    assert balanced_row_range(torch.from_numpy(indptr), 2, 1) == balanced_row_range(indptr, 2, 1)
