@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--e2e-cells", type=int, default=-1,
                     help="cells per GPU for the e2e legs (-1: same as the main leg, reduced only if host RAM cannot hold "
                          "every rank's host matrices; the limit is stated in the JSON)")
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-mofa", action="store_true")

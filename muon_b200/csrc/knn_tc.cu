@@ -115,10 +115,20 @@ __device__ __forceinline__ void tc_compact(float* __restrict__ kb, int32_t* __re
         for (int s = 16; s >= 0; s -= 4) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) hist[j * kTcM + tid] = 0;
-#pragma unroll 4
-            for (int i = 0; i < cnt; ++i) {
-                const uint32_t p = tc_okey(kb[(size_t)i * kTcM + tid]) >> 12;
-                if ((p >> (s + 4)) == H) hist[((p >> s) & 15u) * kTcM + tid] += 1;
+            // eight independent buffer loads in flight, then the (dependent, shared-memory) histogram updates: with one
+            // load per update the compiler cannot move the loads above the updates (generic pointers may alias) and
+            // every element paid a full L2 round trip -- this loop was the whole cost of the candidate pass
+            for (int i = 0; i < cnt; i += 8) {
+                float v8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v8[u] = (i + u < cnt) ? kb[(size_t)(i + u) * kTcM + tid] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (i + u < cnt) {
+                        const uint32_t p = tc_okey(v8[u]) >> 12;
+                        if ((p >> (s + 4)) == H) hist[((p >> s) & 15u) * kTcM + tid] += 1;
+                    }
+                }
             }
             int acc = below, D = 15;
             bool found = false;
@@ -137,13 +147,22 @@ __device__ __forceinline__ void tc_compact(float* __restrict__ kb, int32_t* __re
         if (!(base <= FLT_MAX)) base = FLT_MAX;            // bucket top beyond the finite range (or NaN pattern)
         tau = base + slack;
         int w = 0;
-        for (int i = 0; i < cnt; ++i) {
-            const float v = kb[(size_t)i * kTcM + tid];
-            if (v <= tau) {
-                const int32_t j = ib[(size_t)i * kTcM + tid];
-                kb[(size_t)w * kTcM + tid] = v;
-                ib[(size_t)w * kTcM + tid] = j;
-                ++w;
+        for (int i = 0; i < cnt; i += 8) {                 // same batching: 16 loads in flight, then the in-place writes (w <= i)
+            float v8[8];
+            int32_t j8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = i + u < cnt;
+                v8[u] = ok ? kb[(size_t)(i + u) * kTcM + tid] : 0.f;
+                j8[u] = ok ? ib[(size_t)(i + u) * kTcM + tid] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (i + u < cnt && v8[u] <= tau) {
+                    kb[(size_t)w * kTcM + tid] = v8[u];
+                    ib[(size_t)w * kTcM + tid] = j8[u];
+                    ++w;
+                }
             }
         }
         cnt = w;
