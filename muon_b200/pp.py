@@ -67,14 +67,43 @@ def _umap_connectivities(knn_idx, knn_dist, n_obs):
                       torch.exp(-(d - rho[:, None]) / sigma[:, None]))
     val = torch.where(knn_idx == rows, torch.zeros_like(val), val)
     val = torch.where(knn_idx < 0, torch.zeros_like(val), val)
-    A = sp.coo_matrix((val.cpu().numpy().ravel(), (rows.cpu().numpy().ravel(),
-                                                    knn_idx.clamp_min(0).cpu().numpy().ravel())), shape=(n_obs, n_obs))
-    A.eliminate_zeros()
-    A = A.tocsr()
-    At = A.T.tocsr()
-    out = A + At - A.multiply(At)
-    out.eliminate_zeros()
-    return out.tocsr()
+    # fuzzy union A + A^T - A.A^T on the device: the entries of A and of A^T keyed by (row, column), sorted; a key
+    # occurs once (one-sided edge: value a) or twice (mutual edge: a + b - a*b, the same float32 operations in the
+    # same order as scipy's (A + A.T) - A.multiply(A.T))
+    r = rows.reshape(-1).to(torch.int64)
+    c = knn_idx.clamp_min(0).reshape(-1).to(torch.int64)
+    v = val.reshape(-1)
+    keep = v != 0
+    r, c, v = r[keep], c[keep], v[keep]
+    keys = torch.cat([r * n_obs + c, c * n_obs + r])
+    vals = torch.cat([v, v])
+    keys, order = torch.sort(keys, stable=True)
+    vals = vals[order]
+    first = torch.ones(keys.numel(), dtype=torch.bool, device=keys.device)
+    first[1:] = keys[1:] != keys[:-1]
+    second = ~first
+    pos = torch.nonzero(first).reshape(-1)
+    a = vals[pos]
+    out_val = a.clone()
+    has_pair = torch.zeros(pos.numel(), dtype=torch.bool, device=keys.device)
+    seg_of_second = torch.cumsum(first.to(torch.int64), 0)[second] - 1
+    has_pair[seg_of_second] = True
+    b = torch.zeros_like(a)
+    b[seg_of_second] = vals[second]
+    out_val = torch.where(has_pair, (a + b) - a * b, a)
+    out_key = keys[pos]
+    nz = out_val != 0
+    out_key, out_val = out_key[nz], out_val[nz]
+    out_rows = torch.div(out_key, n_obs, rounding_mode="floor")
+    out_cols = (out_key - out_rows * n_obs).to(torch.int32)
+    indptr = torch.zeros(n_obs + 1, dtype=torch.int64, device=keys.device)
+    indptr[1:] = torch.cumsum(torch.bincount(out_rows, minlength=n_obs), 0)
+    out = sp.csr_matrix((n_obs, n_obs), dtype=np.float32)
+    idt = np.int32 if int(indptr[-1]) < 2**31 - 1 else np.int64
+    out.data, out.indices, out.indptr = out_val.cpu().numpy(), out_cols.cpu().numpy().astype(idt, copy=False), \
+        indptr.cpu().numpy().astype(idt, copy=False)
+    out.has_sorted_indices = True
+    return out
 
 
 def neighbors(
