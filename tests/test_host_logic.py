@@ -333,3 +333,31 @@ def test_nnz_balanced_row_blocks():
         for r0, r1 in blocks:
             assert abs((indptr[r1] - indptr[r0]) - share) <= lens.max() + 1
     assert balanced_row_range(torch.from_numpy(indptr), 2, 1) == balanced_row_range(indptr, 2, 1)
+
+
+def test_row_chunk_and_upload_block_boundaries():
+    """Host-side geometry the tiled kernels rely on: the 16 row chunks are aligned to the tiled kernels' block height
+    (a CTA never straddles a chunk), nest into 1/2/4/8/16 panels, and the upload blocks of the host path are cut on
+    the same alignment while covering every row exactly once."""
+    from muon_b200 import _device
+    R = _device.tile_rows()
+    assert R == 512
+    for n in (1, 300, 512, 5000, 20_000, 1_000_000, 1_234_567):
+        cb = _device.chunk_bounds(n)
+        assert len(cb) == _device.N_CHUNKS + 1 and cb[0] == 0 and cb[-1] == n
+        assert all(a <= b for a, b in zip(cb, cb[1:])) and all(b % R == 0 or b == n for b in cb)
+        for n_panels in (1, 2, 4, 8, 16):
+            per = _device.N_CHUNKS // n_panels
+            pb = [cb[i * per] for i in range(n_panels)] + [n]
+            assert pb[0] == 0 and pb[-1] == n and all(a <= b for a, b in zip(pb, pb[1:]))
+    rng = np.random.default_rng(0)
+    lens = rng.integers(0, 4000, 7000)
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    blocks = _device._row_blocks(indptr, 1_000_000, R)
+    assert blocks[0][0] == 0 and blocks[-1][1] == 7000
+    for (r0, r1, k0, k1), nxt in zip(blocks, blocks[1:] + [None]):
+        assert r0 % R == 0 and r1 > r0 and k0 == indptr[r0] and k1 == indptr[r1]
+        if nxt is not None:
+            assert nxt[0] == r1
+    assert _device._row_blocks(indptr[:1], 10, R) == []
+    assert _device.sample_row_blocks(200_000) and sum(b - a for a, b in _device.sample_row_blocks(200_000)) == 200_000 // 16
