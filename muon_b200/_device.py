@@ -741,9 +741,10 @@ def gram(Y: torch.Tensor, l: Optional[int] = None, weights: Optional[torch.Tenso
 # ------------------------------------------------------------------------------------------
 # Host path of tfidf(): pageable scipy CSR in, pageable scipy CSR out (the reference's contract,
 # muon/_atac/preproc.py:86-129), with the device work hidden under the transfers:
-#   upload  row block b+1 is staged/uploaded on a copy stream while the reduce kernel runs on block b
-#   download the apply kernel of block b+1 runs while block b's values drain to the host
-# Fingerprints of what crossed the bus are a by-product of the staging copies (csrc/staging.cu).
+#   upload    row block b+1 is staged/uploaded on a copy stream while the reduce kernel runs on block b
+#             (int64 indices -> int32 and float32 counts -> uint8 inside the staging copy)
+#   download  one apply launch over all rows (20 ms), then one staged download into a recycled host buffer
+# Fingerprints of what crossed the bus are taken on the device copies afterwards (csrc/staging.cu).
 _BLOCK_NNZ = int(os.environ.get("MUON_B200_BLOCK_NNZ", str(192 << 20)))
 
 
@@ -797,7 +798,6 @@ def tfidf_from_host(X, log_tf=True, log_idf=True, log_tfidf=False, scale_factor=
     side.wait_stream(main)                      # allocations above are ordered on the main stream
     narrow = indices_h.dtype == np.int64
     assert narrow or indices_h.dtype == np.int32, indices_h.dtype
-    fp_idx, fp_out = [], []
     # peak counts are small integers stored as float32: they cross the bus as uint8 (a quarter of the bytes) and are
     # widened on the device; the first block that holds anything else switches this off for the rest of the matrix
     as_u8 = os.environ.get("MUON_B200_COUNTS_U8", "1") != "0"
